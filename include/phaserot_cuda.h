@@ -1,0 +1,195 @@
+/*
+ * libphaserot_cuda — C ABI of the B200 (sm_100a) backend for the phase-rotation
+ * hot path of x42/phaserotate.lv2.
+ *
+ * Plain C, plain pointers and sizes.  Every entry point names the reference
+ * interface it replaces (paths relative to the reference tree, commit 00fece1).
+ * There is no CPU fallback: phaserot_create() fails with PHASEROT_E_NO_DEVICE
+ * when no sm_100 device is usable, and every other call fails on a handle that
+ * could not be created.
+ *
+ * Threading: create/destroy may be called concurrently from any thread (the
+ * reference serialises FFTW planning with a mutex for the same reason,
+ * src/phaserotate.c:43,198-220,358-365).  All other calls on one handle must
+ * come from one thread at a time (an LV2 run() thread, or the CLI main thread).
+ *
+ * Memory: the caller owns every host buffer passed in; the library owns device
+ * memory, pinned staging buffers and streams.  Pointers documented as "device"
+ * must be CUDA device pointers on the handle's device.
+ */
+#ifndef PHASEROT_CUDA_H
+#define PHASEROT_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define PHASEROT_API __declspec(dllexport)
+#else
+#define PHASEROT_API __attribute__ ((visibility ("default")))
+#endif
+
+#define PHASEROT_ABI_VERSION 1
+
+typedef struct phaserot phaserot_t;
+
+enum {
+	PHASEROT_OK            = 0,
+	PHASEROT_E_INVAL       = -1, /* bad argument */
+	PHASEROT_E_NO_DEVICE   = -2, /* no usable sm_100 GPU: there is no CPU fallback */
+	PHASEROT_E_CUDA        = -3, /* a CUDA call failed; see phaserot_last_error() */
+	PHASEROT_E_NOMEM       = -4, /* host or device allocation failed */
+	PHASEROT_E_UNSUPPORTED = -5, /* valid for the reference but not implemented on the device path yet */
+	PHASEROT_E_STATE       = -6  /* call not valid for this handle's mode */
+};
+
+enum {
+	/* Mirrors cli/phase-rotate.cc: FIR length = block size, PhaseRotate semantics. */
+	PHASEROT_MODE_CLI = 0,
+	/* Mirrors src/phaserotate.c: sizes from the sample rate (src:278-297), run() semantics. */
+	PHASEROT_MODE_PLUGIN = 1
+};
+
+enum {
+	/* Default (0): bug-compatible with the reference.  Flags switch single
+	 * quirks off. */
+	PHASEROT_FLAG_NO_FIRST_BLOCK_QUIRK = 1u << 0, /* Q1: test the first L/2 outputs against the real history */
+	PHASEROT_FLAG_NO_PRUNE             = 1u << 1  /* evaluate every sample at every angle (no exact pruning) */
+};
+
+typedef struct phaserot_cfg {
+	uint32_t abi_version; /* PHASEROT_ABI_VERSION */
+	int32_t  mode;        /* PHASEROT_MODE_* */
+	int32_t  n_channels;  /* CLI: SF_INFO.channels (cli:770-777); plugin: 1 or 2 (src/phaserotate.h:97) */
+	int32_t  blksiz;      /* CLI: process block = FIR length, power of two in [1024, 32768] (cli:749-755) */
+	double   sample_rate; /* plugin: rate passed to instantiate() (src:278-289) */
+	int32_t  subsample;   /* angle grid: MAXSAMPLE = 180 * subsample; 0 -> 2 = the reference grid (cli:38-39) */
+	int32_t  device;      /* CUDA device ordinal, -1 = current device */
+	uint32_t flags;       /* PHASEROT_FLAG_* */
+} phaserot_cfg_t;
+
+/* ---- lifetime ---------------------------------------------------------- */
+
+/* Replaces: PhaseRotateProc + PhaseRotate construction (cli:128-165, 314-335,
+ * 768-777) in CLI mode; the DSP part of instantiate() (src:278-404) in plugin
+ * mode.  Designs the Hilbert FIR (same taps as the reference), uploads its
+ * spectrum and allocates stream state.  Returns PHASEROT_OK or a negative
+ * error; *out is NULL on failure. */
+PHASEROT_API int phaserot_create (phaserot_t** out, const phaserot_cfg_t* cfg);
+
+/* Replaces: ~PhaseRotate / ~PhaseRotateProc (cli:167-173, 337-353); cleanup() (src:179-223). */
+PHASEROT_API void phaserot_destroy (phaserot_t* h);
+
+/* Replaces: PhaseRotate::reset (cli:355-366) / activate() (src:511-520):
+ * clears stream history, overlap state and the peak table.  The plugin's angle
+ * state is NOT reset, like the reference (src:147,169-177). */
+PHASEROT_API int phaserot_reset (phaserot_t* h);
+
+/* Run all work of this handle on a caller-owned CUDA stream (cudaStream_t),
+ * e.g. the stream a framework times with its own events.  NULL restores the
+ * handle's private stream. */
+PHASEROT_API int phaserot_set_stream (phaserot_t* h, void* cuda_stream);
+
+/* ---- CLI analysis: min-peak sweep -------------------------------------- */
+
+/* Replaces: one analyze_file() pass (cli:565-587) = PhaseRotate::analyze over
+ * every block of the file plus the zero flush block, including the first-block
+ * rule (cli:418-419) and the raw-peak rule for un-wrapped angle 0 (cli:413-414).
+ *
+ *   interleaved : n_frames * n_channels floats, host memory (pinned is faster)
+ *   ang_start, ang_end, ang_stride : the angle loop of thr_process (cli:409-428),
+ *                 in grid steps (half degrees for subsample 2)
+ *   chn         : -1 = all channels, else only that channel (cli:434-435)
+ *
+ * Results accumulate (max) into the handle's peak table exactly like
+ * PhaseRotate::_peak; read them with phaserot_peak()/phaserot_peaks().
+ * Synchronous: the table is final when the call returns. */
+PHASEROT_API int phaserot_sweep (phaserot_t* h, const float* interleaved, uint64_t n_frames,
+                                 int ang_start, int ang_end, int ang_stride, int chn);
+
+/* Same pass over audio that is already resident in device memory
+ * (interleaved, n_frames * n_channels floats).  Work is enqueued on the
+ * handle's stream; the peak table is brought back by the next
+ * phaserot_peak()/phaserot_peaks()/phaserot_sync() call. */
+PHASEROT_API int phaserot_sweep_device (phaserot_t* h, const float* d_interleaved, uint64_t n_frames,
+                                        int ang_start, int ang_end, int ang_stride, int chn);
+
+/* Block-streaming drop-in for PhaseRotate::analyze (cli:431-444): feed one
+ * block of blksiz frames at a time (`start` != 0 for the first block of a
+ * file, cli:571-582).  Blocks are staged and processed in large batches; the
+ * peak table is completed by the next phaserot_peak()/phaserot_peaks() call.
+ * The angle range must stay the same between two reads of the table. */
+PHASEROT_API int phaserot_analyze (phaserot_t* h, const float* block, int ang_start, int ang_end,
+                                   int ang_stride, int chn, int start);
+
+/* Replaces: PhaseRotate::peak (cli:275-285), incl. c < 0 -> peak_all (cli:287-299). */
+PHASEROT_API float phaserot_peak (phaserot_t* h, int c, int a);
+
+/* Whole table: out[n_channels][180 * subsample]. */
+PHASEROT_API int phaserot_peaks (phaserot_t* h, float* out);
+
+/* sin/cos of the angle grid as used for every rotation: the reference's
+ * SinCosLut (cli:41-72).  s, c: [180 * subsample]. */
+PHASEROT_API int phaserot_lut (phaserot_t* h, float* s, float* c);
+
+/* ---- CLI render -------------------------------------------------------- */
+
+/* Replaces: PhaseRotate::apply (cli:467-485) — one block of blksiz frames,
+ * in place, interleaved; angles[c] in grid steps, wrapped like cli:463.
+ * Stateful (history + overlap), synchronous. */
+PHASEROT_API int phaserot_apply (phaserot_t* h, float* buf, const int* angles);
+
+/* Bulk form of the same stream: processes ceil(n_frames / blksiz) zero padded
+ * blocks plus `flush_blocks` zero blocks from reset state in one device pass.
+ * out: (ceil(n_frames / blksiz) + flush_blocks) * blksiz frames, interleaved,
+ * no latency trim (the trim stays in the host write loop, cli:963-1001). */
+PHASEROT_API int phaserot_render (phaserot_t* h, const float* interleaved, uint64_t n_frames,
+                                  const int* angles, int flush_blocks, float* out);
+
+/* Device-resident form: d_in / d_out are device pointers (same shapes). */
+PHASEROT_API int phaserot_render_device (phaserot_t* h, const float* d_interleaved, uint64_t n_frames,
+                                         const int* angles, int flush_blocks, float* d_out);
+
+/* ---- plugin ------------------------------------------------------------ */
+
+/* Replaces: the audio path of run() -> process_channel() (src:538-725, 774-852)
+ * for all channels of the instance: planar in[c] / out[c] of n_frames floats
+ * (in[c] == out[c] allowed, src:780-785), angle_deg[c] = value of the angle
+ * control port for this call (src:564-571).  Keeps the reference's latency
+ * (phaserot_latency()) and its per-partition angle ramp (src:673-717).
+ * Synchronous; no host allocation in steady state. */
+PHASEROT_API int phaserot_process (phaserot_t* h, const float* const* in, float* const* out,
+                                   uint32_t n_frames, const float* angle_deg);
+
+/* Replaces: FFTiProc::latency = parsiz + firlat (src:297); CLI: blksiz / 2 (cli:963). */
+PHASEROT_API uint32_t phaserot_latency (const phaserot_t* h);
+
+/* ---- misc -------------------------------------------------------------- */
+
+/* Wait for all enqueued work of this handle and bring the peak table back. */
+PHASEROT_API int phaserot_sync (phaserot_t* h);
+
+/* Counters since create/reset_stats: kernels launched by this library and
+ * sample-angle pairs actually evaluated after exact pruning. */
+typedef struct phaserot_stats {
+	uint64_t kernel_launches;
+	uint64_t points_total;     /* (channel, sample) pairs examined by the sweep filter */
+	uint64_t points_evaluated; /* pairs that survived pruning and were evaluated at every angle */
+	uint64_t h2d_bytes;
+	uint64_t d2h_bytes;
+} phaserot_stats_t;
+PHASEROT_API int phaserot_get_stats (phaserot_t* h, phaserot_stats_t* out);
+PHASEROT_API int phaserot_reset_stats (phaserot_t* h);
+
+PHASEROT_API const char* phaserot_strerror (int code);
+/* Text of the last CUDA failure on this thread ("" if none). */
+PHASEROT_API const char* phaserot_last_error (void);
+PHASEROT_API int         phaserot_abi_version (void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,226 @@
+"""ctypes binding of libphaserot_cuda (include/phaserot_cuda.h).
+
+This is plumbing for tests and bench.py: it forwards to the C ABI and never
+computes audio itself.  If the library is missing or no sm_100 GPU is present
+every entry point fails loudly (PhaserotError) — there is no CPU fallback.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+OK = 0
+E_INVAL, E_NO_DEVICE, E_CUDA, E_NOMEM, E_UNSUPPORTED, E_STATE = -1, -2, -3, -4, -5, -6
+MODE_CLI, MODE_PLUGIN = 0, 1
+FLAG_NO_FIRST_BLOCK_QUIRK = 1
+FLAG_NO_PRUNE = 2
+ABI_VERSION = 1
+
+SYMBOLS = [
+    "phaserot_create", "phaserot_destroy", "phaserot_reset", "phaserot_set_stream",
+    "phaserot_sweep", "phaserot_sweep_device", "phaserot_analyze", "phaserot_peak", "phaserot_peaks", "phaserot_lut",
+    "phaserot_apply", "phaserot_render", "phaserot_render_device",
+    "phaserot_process", "phaserot_latency",
+    "phaserot_sync", "phaserot_get_stats", "phaserot_reset_stats",
+    "phaserot_strerror", "phaserot_last_error", "phaserot_abi_version",
+]
+
+
+class Cfg(C.Structure):
+    _fields_ = [
+        ("abi_version", C.c_uint32), ("mode", C.c_int32), ("n_channels", C.c_int32), ("blksiz", C.c_int32),
+        ("sample_rate", C.c_double), ("subsample", C.c_int32), ("device", C.c_int32), ("flags", C.c_uint32),
+    ]
+
+
+class Stats(C.Structure):
+    _fields_ = [("kernel_launches", C.c_uint64), ("points_total", C.c_uint64), ("points_evaluated", C.c_uint64),
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+
+
+class PhaserotError(RuntimeError):
+    def __init__(self, code, what, detail=""):
+        self.code = code
+        super().__init__(f"{what}: {code} ({detail})")
+
+
+_lib = None
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load():
+    """Load (building first if the sources are newer) libphaserot_cuda.so."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if not os.path.exists(path):
+        _build.build_library()
+    lib = C.CDLL(path)
+    vp, fp, ip = C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)
+    lib.phaserot_create.argtypes = [C.POINTER(vp), C.POINTER(Cfg)]
+    lib.phaserot_destroy.argtypes = [vp]
+    lib.phaserot_destroy.restype = None
+    lib.phaserot_reset.argtypes = [vp]
+    lib.phaserot_set_stream.argtypes = [vp, vp]
+    lib.phaserot_sweep.argtypes = [vp, vp, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.phaserot_sweep_device.argtypes = [vp, vp, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.phaserot_analyze.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.phaserot_peak.argtypes = [vp, C.c_int, C.c_int]
+    lib.phaserot_peak.restype = C.c_float
+    lib.phaserot_peaks.argtypes = [vp, vp]
+    lib.phaserot_lut.argtypes = [vp, vp, vp]
+    lib.phaserot_apply.argtypes = [vp, vp, vp]
+    lib.phaserot_render.argtypes = [vp, vp, C.c_uint64, vp, C.c_int, vp]
+    lib.phaserot_render_device.argtypes = [vp, vp, C.c_uint64, vp, C.c_int, vp]
+    lib.phaserot_process.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.c_uint32, vp]
+    lib.phaserot_latency.argtypes = [vp]
+    lib.phaserot_latency.restype = C.c_uint32
+    lib.phaserot_sync.argtypes = [vp]
+    lib.phaserot_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    lib.phaserot_reset_stats.argtypes = [vp]
+    lib.phaserot_strerror.argtypes = [C.c_int]
+    lib.phaserot_strerror.restype = C.c_char_p
+    lib.phaserot_last_error.restype = C.c_char_p
+    lib.phaserot_abi_version.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Phaserot:
+    """Thin RAII wrapper: one libphaserot_cuda handle."""
+
+    def __init__(self, mode=MODE_CLI, n_channels=1, blksiz=8192, sample_rate=48000.0, subsample=2, device=-1, flags=0):
+        self._lib = load()
+        self._h = C.c_void_p()
+        self.n_channels, self.blksiz, self.subsample, self.mode = n_channels, blksiz, subsample or 2, mode
+        self.maxsample = 180 * self.subsample
+        cfg = Cfg(ABI_VERSION, mode, n_channels, blksiz, float(sample_rate), subsample, device, flags)
+        rc = self._lib.phaserot_create(C.byref(self._h), C.byref(cfg))
+        if rc != OK:
+            self._h = C.c_void_p()
+            raise PhaserotError(rc, "phaserot_create", self._detail(rc))
+
+    def _detail(self, rc):
+        return self._lib.phaserot_strerror(rc).decode() + "; " + self._lib.phaserot_last_error().decode()
+
+    def _ck(self, rc, what):
+        if rc != OK:
+            raise PhaserotError(rc, what, self._detail(rc))
+
+    def close(self):
+        if self._h:
+            self._lib.phaserot_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- CLI analysis ------------------------------------------------------
+    def reset(self):
+        self._ck(self._lib.phaserot_reset(self._h), "phaserot_reset")
+
+    def set_stream(self, stream_ptr):
+        self._ck(self._lib.phaserot_set_stream(self._h, C.c_void_p(stream_ptr)), "phaserot_set_stream")
+
+    def sweep(self, x, ang_start=0, ang_end=None, stride=1, chn=-1):
+        """x: host array [frames, channels] float32 (C-contiguous) or a raw host pointer tuple (ptr, frames)."""
+        if ang_end is None:
+            ang_end = self.maxsample
+        if isinstance(x, tuple):
+            ptr, n = x
+        else:
+            x = np.ascontiguousarray(x, np.float32).reshape(-1, self.n_channels)
+            ptr, n = x.ctypes.data, x.shape[0]
+        self._ck(self._lib.phaserot_sweep(self._h, C.c_void_p(ptr), n, ang_start, ang_end, stride, chn), "phaserot_sweep")
+
+    def sweep_device(self, dev_ptr, n_frames, ang_start=0, ang_end=None, stride=1, chn=-1):
+        if ang_end is None:
+            ang_end = self.maxsample
+        self._ck(self._lib.phaserot_sweep_device(self._h, C.c_void_p(dev_ptr), n_frames, ang_start, ang_end, stride, chn), "phaserot_sweep_device")
+
+    def analyze(self, block, ang_start=0, ang_end=180, stride=1, chn=-1, start=False):
+        block = np.ascontiguousarray(block, np.float32)
+        assert block.size == self.blksiz * self.n_channels
+        self._ck(self._lib.phaserot_analyze(self._h, _ptr(block), ang_start, ang_end, stride, chn, int(start)), "phaserot_analyze")
+
+    def peak(self, c, a):
+        return float(self._lib.phaserot_peak(self._h, c, a))
+
+    def peaks(self):
+        out = np.zeros((self.n_channels, self.maxsample), np.float32)
+        self._ck(self._lib.phaserot_peaks(self._h, _ptr(out)), "phaserot_peaks")
+        return out
+
+    def lut(self):
+        s = np.zeros(self.maxsample, np.float32)
+        c = np.zeros(self.maxsample, np.float32)
+        self._ck(self._lib.phaserot_lut(self._h, _ptr(s), _ptr(c)), "phaserot_lut")
+        return s, c
+
+    def sync(self):
+        self._ck(self._lib.phaserot_sync(self._h), "phaserot_sync")
+
+    # -- CLI render --------------------------------------------------------
+    def apply(self, buf, angles):
+        buf = np.ascontiguousarray(buf, np.float32)
+        ang = np.ascontiguousarray(angles, np.int32)
+        self._ck(self._lib.phaserot_apply(self._h, _ptr(buf), _ptr(ang)), "phaserot_apply")
+        return buf
+
+    def render(self, x, angles, flush_blocks=1):
+        x = np.ascontiguousarray(x, np.float32).reshape(-1, self.n_channels)
+        n = x.shape[0]
+        nblk = (n + self.blksiz - 1) // self.blksiz + flush_blocks
+        out = np.zeros((nblk * self.blksiz, self.n_channels), np.float32)
+        ang = np.ascontiguousarray(angles, np.int32)
+        self._ck(self._lib.phaserot_render(self._h, _ptr(x), n, _ptr(ang), flush_blocks, _ptr(out)), "phaserot_render")
+        return out
+
+    def render_device(self, d_in, n_frames, angles, flush_blocks, d_out):
+        ang = np.ascontiguousarray(angles, np.int32)
+        self._ck(self._lib.phaserot_render_device(self._h, C.c_void_p(d_in), n_frames, _ptr(ang), flush_blocks, C.c_void_p(d_out)), "phaserot_render_device")
+
+    # -- plugin ------------------------------------------------------------
+    def process(self, x_planar, angle_deg):
+        """x_planar: [channels, n] float32; returns output of the same shape."""
+        x = np.ascontiguousarray(x_planar, np.float32).reshape(self.n_channels, -1)
+        out = np.zeros_like(x)
+        n = x.shape[1]
+        ins = (C.c_void_p * self.n_channels)(*[x[c].ctypes.data for c in range(self.n_channels)])
+        outs = (C.c_void_p * self.n_channels)(*[out[c].ctypes.data for c in range(self.n_channels)])
+        ang = np.ascontiguousarray(np.broadcast_to(np.asarray(angle_deg, np.float32), (self.n_channels,)))
+        self._ck(self._lib.phaserot_process(self._h, ins, outs, n, _ptr(ang)), "phaserot_process")
+        return out
+
+    def process_raw(self, in_ptrs, out_ptrs, n, ang):
+        self._ck(self._lib.phaserot_process(self._h, in_ptrs, out_ptrs, n, _ptr(ang)), "phaserot_process")
+
+    def latency(self):
+        return int(self._lib.phaserot_latency(self._h))
+
+    def stats(self):
+        s = Stats()
+        self._ck(self._lib.phaserot_get_stats(self._h, C.byref(s)), "phaserot_get_stats")
+        return {k: int(getattr(s, k)) for k, _ in Stats._fields_}
+
+    def reset_stats(self):
+        self._ck(self._lib.phaserot_reset_stats(self._h), "phaserot_reset_stats")

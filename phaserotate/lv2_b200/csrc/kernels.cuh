@@ -1,0 +1,572 @@
+// Device code of libphaserot_cuda (sm_100a).
+//
+// K0 deinterleave_kernel   interleaved frames -> planar "complex" planes
+// K1 fftconv_kernel        Hilbert FIR as overlap-save FFT convolution in shared
+//                          memory, with fused epilogues:
+//                            EPI_POINTS  analytic pair (x_d, h) -> exact radius
+//                                        filter -> compacted survivor list
+//                            EPI_RENDER  y = ca * x_d + sa * h  (K4)
+//                            EPI_HILBERT h only (tests / diagnostics)
+// K3 sweep_kernel          every angle over a survivor list, angles in lanes,
+//                          running max in registers, one atomicMax per angle/CTA
+//    threshold_kernel      min over angles of the running peaks -> next filter radius
+//    fir_direct_kernel     small-call plugin path: direct-form FIR + rotate
+//
+// Data layout.  A channel's samples x[0..F) are viewed as complex numbers
+// z[n] = x[2n] + i x[2n+1] ("plane", float2, with a zero front pad).  The
+// reference FIR (cli/phase-rotate.cc:144-161, src/phaserotate.c:374-391) has
+// non-zero taps only at odd k, so with g[j] = fir[2j+1]
+//     w = z (*) g        (complex sequence, real taps, Lh = L/2 taps)
+//     H[2m+1] = Re w[m],  H[2m] = Im w[m-1],
+// i.e. one complex FFT convolution of half the length yields the Hilbert branch
+// of two real samples per point with no real/complex split step.  The delayed
+// direct branch x_d[t] = x[t - L/2] is z[m - Lh/2] (cli:220, src:665-671).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace prk {
+
+constexpr int kLog2M   = 14;
+constexpr int kM       = 1 << kLog2M; // complex FFT size per segment
+constexpr int kConvThreads = 512;
+constexpr int kSmemElems   = kM + (kM >> 6) * 4; // padded: 4 extra float2 per 64
+constexpr int kSmemBytes   = kSmemElems * (int)sizeof (float2);
+
+enum { EPI_POINTS = 0, EPI_RENDER = 1, EPI_HILBERT = 2 };
+
+struct ConvParams {
+	const float2* plane;        // [n_chan][plane_stride], element (padf + n) = z[n]
+	long long     plane_stride;
+	int           padf;
+	const float2* G;            // [kM] filter spectrum / kM, in the forward pass's output order
+	const float2* tw1;          // [6][1024]  W_M^(j q),    q in {1,2,3,4,8,12}
+	const float2* tw2;          // [6][64]    W_1024^(j q)
+	const float2* tw3;          // [6][4]     W_64^(j q)
+	int           Lh;           // half taps = L/2 (multiple of 4)
+	int           V;            // valid complex outputs per segment = kM - Lh
+	int           chan0;        // first channel of this launch
+	long long     seg0;         // first segment
+	long long     nseg;         // segments per channel in this launch
+	int           nchan;
+	long long     m_end;        // outputs exist for complex index m < m_end
+	long long     m_skip;       // m <  m_skip : not examined            (first-block rule, cli:418-419)
+	long long     m_zero;       // m <  m_zero : direct branch forced to 0
+	// EPI_POINTS
+	float2*       list;         // [n_chan][list_stride]
+	long long     list_stride;
+	unsigned*     count;        // [n_chan]
+	const float*  thr2;         // [n_chan] squared filter radius
+	unsigned*     rawpeak;      // [n_chan] bits of max |x|
+	unsigned long long* n_seen; // points examined (stats)
+	// EPI_RENDER / EPI_HILBERT
+	float2*       out;          // [n_chan][out_stride], element m
+	long long     out_stride;
+	const float2* cs;           // [n_chan] (ca, sa) steady state
+	const float2* ramp;         // [n_chan][ramp_stride] per-sample (ca, sa) for t < ramp_len[c]
+	long long     ramp_stride;
+	const int*    ramp_len;     // [n_chan] (in samples, even) or nullptr
+};
+
+// ---------------------------------------------------------------------------
+// small complex helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float2 cadd (float2 a, float2 b) { return make_float2 (a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub (float2 a, float2 b) { return make_float2 (a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul (float2 a, float2 b)
+{
+	return make_float2 (fmaf (a.x, b.x, -a.y * b.y), fmaf (a.x, b.y, a.y * b.x));
+}
+// a * conj(b)
+__device__ __forceinline__ float2 cmulc (float2 a, float2 b)
+{
+	return make_float2 (fmaf (a.x, b.x, a.y * b.y), fmaf (a.y, b.x, -a.x * b.y));
+}
+// multiply by the primitive 4th root used in direction DIR: -i (forward) or +i (inverse)
+template <int DIR>
+__device__ __forceinline__ float2 mulw4 (float2 a)
+{
+	return DIR < 0 ? make_float2 (a.y, -a.x) : make_float2 (-a.y, a.x);
+}
+
+template <int DIR>
+__device__ __forceinline__ void dft4 (float2& a0, float2& a1, float2& a2, float2& a3)
+{
+	const float2 s02 = cadd (a0, a2), d02 = csub (a0, a2);
+	const float2 s13 = cadd (a1, a3), d13 = mulw4<DIR> (csub (a1, a3));
+	a0 = cadd (s02, s13);
+	a2 = csub (s02, s13);
+	a1 = cadd (d02, d13);
+	a3 = csub (d02, d13);
+}
+
+// multiply by exp(DIR * 2 pi i m / 16), m compile-time
+template <int DIR, int m>
+__device__ __forceinline__ float2 mulw16 (float2 a)
+{
+	constexpr float C1 = 0.92387953251128675613f; // cos(pi/8)
+	constexpr float S1 = 0.38268343236508977173f; // sin(pi/8)
+	constexpr float H  = 0.70710678118654752440f;
+	constexpr float sg = DIR < 0 ? -1.f : 1.f;
+	if (m == 0) return a;
+	if (m == 1) return make_float2 (a.x * C1 - a.y * (sg * S1), a.x * (sg * S1) + a.y * C1);
+	if (m == 2) return make_float2 ((a.x - sg * a.y) * H, (sg * a.x + a.y) * H);
+	if (m == 3) return make_float2 (a.x * S1 - a.y * (sg * C1), a.x * (sg * C1) + a.y * S1);
+	if (m == 4) return mulw4<DIR> (a);
+	if (m == 6) return make_float2 ((-a.x - sg * a.y) * H, (sg * a.x - a.y) * H);
+	if (m == 9) return make_float2 (-a.x * C1 + a.y * (sg * S1), -a.x * (sg * S1) - a.y * C1);
+	return a;
+}
+
+// 16-point DFT in registers.  Input u[k] natural order; on return the value
+// y[q] sits in u[(q >> 2) + 4 * (q & 3)].
+template <int DIR>
+__device__ __forceinline__ void dft16 (float2 (&u)[16])
+{
+#pragma unroll
+	for (int k0 = 0; k0 < 4; ++k0) {
+		dft4<DIR> (u[k0], u[k0 + 4], u[k0 + 8], u[k0 + 12]); // u[k0 + 4 ql] = v[k0][ql]
+	}
+	u[5]  = mulw16<DIR, 1> (u[5]);
+	u[9]  = mulw16<DIR, 2> (u[9]);
+	u[13] = mulw16<DIR, 3> (u[13]);
+	u[6]  = mulw16<DIR, 2> (u[6]);
+	u[10] = mulw16<DIR, 4> (u[10]);
+	u[14] = mulw16<DIR, 6> (u[14]);
+	u[7]  = mulw16<DIR, 3> (u[7]);
+	u[11] = mulw16<DIR, 6> (u[11]);
+	u[15] = mulw16<DIR, 9> (u[15]);
+#pragma unroll
+	for (int ql = 0; ql < 4; ++ql) {
+		dft4<DIR> (u[4 * ql], u[4 * ql + 1], u[4 * ql + 2], u[4 * ql + 3]); // u[qh + 4 ql] = y[4 qh + ql]
+	}
+}
+
+__device__ __forceinline__ int phys (int i) { return i + ((i >> 6) << 2); }
+
+// The 15 inter-pass twiddles W^(j q), q = ql + 4 qh, from six table entries.
+struct Tw6 {
+	float2 t1, t2, t3, t4, t8, t12;
+};
+__device__ __forceinline__ Tw6 load_tw (const float2* __restrict__ tw, int stride, int j)
+{
+	Tw6 t;
+	t.t1  = __ldg (tw + j);
+	t.t2  = __ldg (tw + stride + j);
+	t.t3  = __ldg (tw + 2 * stride + j);
+	t.t4  = __ldg (tw + 3 * stride + j);
+	t.t8  = __ldg (tw + 4 * stride + j);
+	t.t12 = __ldg (tw + 5 * stride + j);
+	return t;
+}
+template <bool CONJ>
+__device__ __forceinline__ float2 apply_tw (float2 v, const Tw6& t, int q)
+{
+	const int ql = q & 3, qh = q >> 2;
+	if (ql) {
+		const float2 a = ql == 1 ? t.t1 : ql == 2 ? t.t2 : t.t3;
+		v              = CONJ ? cmulc (v, a) : cmul (v, a);
+	}
+	if (qh) {
+		const float2 b = qh == 1 ? t.t4 : qh == 2 ? t.t8 : t.t12;
+		v              = CONJ ? cmulc (v, b) : cmul (v, b);
+	}
+	return v;
+}
+
+// One radix-16 pass over the whole segment held in shared memory.
+// Butterfly e: block = e / STRIDE (size 16 * STRIDE), j = e % STRIDE.
+// Forward (DIF): u = data[j + k STRIDE]; y = DFT16(u); store y[q] * W^(j q) at q.
+// Inverse (DIT): y[q] * conj W^(j q); u = IDFT16; store u[k] at k.
+template <int DIR, int STRIDE, bool FROM_GLOBAL>
+__device__ __forceinline__ void pass16 (float2* sm, const float2* __restrict__ tw, const float2* __restrict__ gsrc, int tid)
+{
+#pragma unroll 1
+	for (int e = tid; e < kM / 16; e += kConvThreads) {
+		const int blk  = e / STRIDE;
+		const int j    = e - blk * STRIDE;
+		const int base = blk * (16 * STRIDE) + j;
+		float2    u[16];
+		if (FROM_GLOBAL) {
+#pragma unroll
+			for (int k = 0; k < 16; ++k) {
+				u[k] = __ldcs (gsrc + base + k * STRIDE);
+			}
+		} else {
+#pragma unroll
+			for (int k = 0; k < 16; ++k) {
+				u[k] = sm[phys (base + k * STRIDE)];
+			}
+		}
+		const Tw6 t = load_tw (tw, STRIDE, j);
+		if (DIR > 0) {
+#pragma unroll
+			for (int q = 1; q < 16; ++q) {
+				u[q] = apply_tw<true> (u[q], t, q);
+			}
+		}
+		dft16<DIR> (u);
+#pragma unroll
+		for (int q = 0; q < 16; ++q) {
+			float2 v = u[(q >> 2) + 4 * (q & 3)];
+			if (DIR < 0 && q) {
+				v = apply_tw<false> (v, t, q);
+			}
+			sm[phys (base + q * STRIDE)] = v;
+		}
+	}
+}
+
+// Innermost radix-4 forward pass, spectrum multiply, radix-4 inverse pass, all
+// on the same four shared-memory elements.
+__device__ __forceinline__ void mid_pass (float2* sm, const float2* __restrict__ G, int tid)
+{
+#pragma unroll 2
+	for (int e = tid; e < kM / 4; e += kConvThreads) {
+		float4*      p  = reinterpret_cast<float4*> (sm + phys (4 * e));
+		float4       v0 = p[0], v1 = p[1];
+		const float4 g0 = __ldg (reinterpret_cast<const float4*> (G + 4 * e));
+		const float4 g1 = __ldg (reinterpret_cast<const float4*> (G + 4 * e) + 1);
+		float2       a0 = make_float2 (v0.x, v0.y), a1 = make_float2 (v0.z, v0.w);
+		float2       a2 = make_float2 (v1.x, v1.y), a3 = make_float2 (v1.z, v1.w);
+		dft4<-1> (a0, a1, a2, a3);
+		a0 = cmul (a0, make_float2 (g0.x, g0.y));
+		a1 = cmul (a1, make_float2 (g0.z, g0.w));
+		a2 = cmul (a2, make_float2 (g1.x, g1.y));
+		a3 = cmul (a3, make_float2 (g1.z, g1.w));
+		dft4<+1> (a0, a1, a2, a3);
+		p[0] = make_float4 (a0.x, a0.y, a1.x, a1.y);
+		p[1] = make_float4 (a2.x, a2.y, a3.x, a3.y);
+	}
+}
+
+__device__ __forceinline__ unsigned lanemask_lt ()
+{
+	unsigned m;
+	asm ("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+	return m;
+}
+
+// ---------------------------------------------------------------------------
+// K1: FFT convolution with fused epilogue.  Persistent: one CTA per SM walks
+// (channel, segment) pairs.
+// ---------------------------------------------------------------------------
+template <int EPI>
+__global__ void __launch_bounds__ (kConvThreads, 1) fftconv_kernel (const ConvParams p)
+{
+	extern __shared__ __align__ (16) float2 sm[];
+	const int tid = threadIdx.x;
+
+	float     rawmax    = 0.f;
+	int       raw_chan  = -1;
+	unsigned  seen      = 0;
+
+	const long long total = p.nseg * p.nchan;
+	for (long long w = blockIdx.x; w < total; w += gridDim.x) {
+		const int       ci  = (int)(w / p.nseg);
+		const long long seg = p.seg0 + (w - (long long)ci * p.nseg);
+		const int       c   = p.chan0 + ci;
+		// segment input: z[seg V - Lh .. seg V - Lh + M)
+		const float2* zc  = p.plane + (long long)c * p.plane_stride + p.padf;
+		const float2* src = zc + seg * p.V - p.Lh;
+
+		if (EPI == EPI_POINTS && c != raw_chan) {
+			if (raw_chan >= 0) {
+				// flush running raw peak of the previous channel
+				for (int o = 16; o; o >>= 1) rawmax = fmaxf (rawmax, __shfl_xor_sync (0xffffffffu, rawmax, o));
+				if ((tid & 31) == 0) atomicMax (p.rawpeak + raw_chan, __float_as_uint (rawmax));
+			}
+			raw_chan = c;
+			rawmax   = 0.f;
+		}
+
+		pass16<-1, 1024, true> (sm, p.tw1, src, tid);
+		__syncthreads ();
+		pass16<-1, 64, false> (sm, p.tw2, nullptr, tid);
+		__syncthreads ();
+		pass16<-1, 4, false> (sm, p.tw3, nullptr, tid);
+		__syncthreads ();
+		mid_pass (sm, p.G, tid);
+		__syncthreads ();
+		pass16<+1, 4, false> (sm, p.tw3, nullptr, tid);
+		__syncthreads ();
+		pass16<+1, 64, false> (sm, p.tw2, nullptr, tid);
+		__syncthreads ();
+		pass16<+1, 1024, false> (sm, p.tw1, nullptr, tid);
+		__syncthreads ();
+
+		// epilogue over the V valid outputs: local index i in [Lh, M), m = seg V + (i - Lh)
+		const long long mbase = seg * p.V - p.Lh; // m = mbase + i
+		if (EPI == EPI_POINTS) {
+			const float thr2 = p.thr2[c];
+			float2*     lst  = p.list + (long long)c * p.list_stride;
+			unsigned*   cnt  = p.count + c;
+			const unsigned lt = lanemask_lt ();
+			for (int i0 = p.Lh; i0 < kM; i0 += kConvThreads) {
+				const int       i  = i0 + tid;
+				const long long m  = mbase + i;
+				bool            k0 = false, k1 = false;
+				float2          p0 = make_float2 (0.f, 0.f), p1 = p0;
+				if (m < p.m_end) {
+					const float2 c1 = sm[phys (i)];
+					const float2 c0 = sm[phys (i - 1)];
+					float2       zd = __ldg (zc + (m - (p.Lh >> 1)));
+					rawmax          = fmaxf (rawmax, fmaxf (fabsf (zd.x), fabsf (zd.y)));
+					if (m >= p.m_skip) {
+						if (m < p.m_zero) zd = make_float2 (0.f, 0.f);
+						p0 = make_float2 (zd.x, c0.y); // t = 2m   : (x_d, H)
+						p1 = make_float2 (zd.y, c1.x); // t = 2m+1
+						k0 = fmaf (p0.x, p0.x, p0.y * p0.y) >= thr2;
+						k1 = fmaf (p1.x, p1.x, p1.y * p1.y) >= thr2;
+						seen += 2;
+					}
+				}
+				const unsigned b0 = __ballot_sync (0xffffffffu, k0);
+				const unsigned b1 = __ballot_sync (0xffffffffu, k1);
+				if (b0 | b1) {
+					const int n0 = __popc (b0), n1 = __popc (b1);
+					unsigned  base = 0;
+					if ((tid & 31) == 0) base = atomicAdd (cnt, (unsigned)(n0 + n1));
+					base = __shfl_sync (0xffffffffu, base, 0);
+					if (k0) lst[base + __popc (b0 & lt)] = p0;
+					if (k1) lst[base + n0 + __popc (b1 & lt)] = p1;
+				}
+			}
+		} else {
+			float2*      outc = p.out + (long long)c * p.out_stride;
+			const float2 cs   = (EPI == EPI_RENDER) ? p.cs[c] : make_float2 (0.f, 1.f);
+			const int    rlen = (EPI == EPI_RENDER && p.ramp_len) ? p.ramp_len[c] : 0;
+			for (int i = p.Lh + tid; i < kM; i += kConvThreads) {
+				const long long m = mbase + i;
+				if (m < p.m_end) {
+					const float2 c1 = sm[phys (i)];
+					const float2 c0 = sm[phys (i - 1)];
+					float2       y  = make_float2 (c0.y, c1.x);
+					if (EPI == EPI_RENDER) {
+						const float2 zd  = __ldg (zc + (m - (p.Lh >> 1)));
+						float2       cs0 = cs, cs1 = cs;
+						if (2 * m < rlen) {
+							const float2* r = p.ramp + (long long)c * p.ramp_stride + 2 * m;
+							cs0             = r[0];
+							if (2 * m + 1 < rlen) cs1 = r[1];
+						}
+						// mul, mul, add like the reference (cli:223, src:700,715)
+						y.x = __fadd_rn (__fmul_rn (cs0.x, zd.x), __fmul_rn (cs0.y, c0.y));
+						y.y = __fadd_rn (__fmul_rn (cs1.x, zd.y), __fmul_rn (cs1.y, c1.x));
+					}
+					__stcs (outc + m, y);
+				}
+			}
+		}
+		__syncthreads (); // smem is overwritten by the next segment's first pass
+	}
+
+	if (EPI == EPI_POINTS) {
+		if (raw_chan >= 0) {
+			for (int o = 16; o; o >>= 1) rawmax = fmaxf (rawmax, __shfl_xor_sync (0xffffffffu, rawmax, o));
+			if ((tid & 31) == 0) atomicMax (p.rawpeak + raw_chan, __float_as_uint (rawmax));
+		}
+		if (p.n_seen) {
+			for (int o = 16; o; o >>= 1) seen += __shfl_xor_sync (0xffffffffu, seen, o);
+			if ((tid & 31) == 0 && seen) atomicAdd (p.n_seen, (unsigned long long)seen);
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------
+// K0: interleaved frames -> planes.  One thread per complex element n of a
+// chunk: frames 2n and 2n+1 of every channel.  Frames >= n_frames read as 0.
+// ---------------------------------------------------------------------------
+__global__ void deinterleave_kernel (const float* __restrict__ in, long long frame0, long long n_frames_total,
+                                     long long n_first, long long n_count, int C,
+                                     float2* __restrict__ plane, long long plane_stride, int padf)
+{
+	const long long n = n_first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (n >= n_first + n_count) return;
+	const long long f0 = 2 * n, f1 = 2 * n + 1;
+	// `in` points at frame `frame0` of the stream
+	const float* a = in + (f0 - frame0) * C;
+	if (C == 2 && f1 < n_frames_total) {
+		const float4 v = *reinterpret_cast<const float4*> (a);
+		plane[padf + n]                = make_float2 (v.x, v.z);
+		plane[plane_stride + padf + n] = make_float2 (v.y, v.w);
+		return;
+	}
+	for (int c = 0; c < C; ++c) {
+		const float x0 = f0 < n_frames_total ? a[c] : 0.f;
+		const float x1 = f1 < n_frames_total ? a[C + c] : 0.f;
+		plane[(long long)c * plane_stride + padf + n] = make_float2 (x0, x1);
+	}
+}
+
+// planes of float2 (two consecutive samples) -> interleaved frames
+__global__ void interleave_kernel (const float2* __restrict__ plane, long long plane_stride, int C,
+                                   long long n_count, float* __restrict__ out, long long n_frames_out)
+{
+	const long long n = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (n >= n_count) return;
+	const long long f0 = 2 * n, f1 = f0 + 1;
+	if (C == 2 && f1 < n_frames_out) {
+		const float2 l = plane[n], r = plane[plane_stride + n];
+		*reinterpret_cast<float4*> (out + f0 * 2) = make_float4 (l.x, r.x, l.y, r.y);
+		return;
+	}
+	for (int c = 0; c < C; ++c) {
+		const float2 v = plane[(long long)c * plane_stride + n];
+		if (f0 < n_frames_out) out[f0 * C + c] = v.x;
+		if (f1 < n_frames_out) out[f1 * C + c] = v.y;
+	}
+}
+
+// ---------------------------------------------------------------------------
+// K3: sweep.  Thread t of a CTA owns angles a = agrp + t + blockDim * r, r < R:
+// (ca, sa) and the running max stay in registers; the survivor points are
+// broadcast from shared memory.  Replaces calc_rotated_peak (cli:98-121) and
+// dsp_compute_peak (cli/dsp_peak_calc.h): max_i |ca x_d[i] + sa h[i]|.
+// grid = (point tiles, angle groups, channels).
+// ---------------------------------------------------------------------------
+constexpr int kSweepTile = 256; // points per tile
+
+template <int R>
+__global__ void __launch_bounds__ (256) sweep_kernel (const float2* __restrict__ list, long long list_stride,
+                                                       const unsigned* __restrict__ count, int chan0,
+                                                       const float2* __restrict__ cs, int A,
+                                                       unsigned* __restrict__ peaks, int peaks_stride,
+                                                       unsigned long long* __restrict__ n_eval)
+{
+	__shared__ __align__ (16) float2 tile[kSweepTile];
+	const int       c    = chan0 + blockIdx.z;
+	const unsigned  n    = count[c];
+	const float2*   pts  = list + (long long)c * list_stride;
+	const int       a0   = blockIdx.y * (blockDim.x * R) + threadIdx.x;
+
+	float ca[R], sa[R], pk[R];
+#pragma unroll
+	for (int r = 0; r < R; ++r) {
+		const int a = a0 + r * blockDim.x;
+		const float2 v = a < A ? cs[a] : make_float2 (0.f, 0.f);
+		ca[r] = v.x;
+		sa[r] = v.y;
+		pk[r] = 0.f;
+	}
+
+	for (unsigned base = blockIdx.x * kSweepTile; base < n; base += gridDim.x * kSweepTile) {
+		const unsigned cnt = min ((unsigned)kSweepTile, n - base);
+		__syncthreads ();
+		for (unsigned i = threadIdx.x; i < kSweepTile; i += blockDim.x) {
+			tile[i] = i < cnt ? pts[base + i] : make_float2 (0.f, 0.f);
+		}
+		__syncthreads ();
+		const float4* t4 = reinterpret_cast<const float4*> (tile);
+		const unsigned n2 = (cnt + 1) >> 1;
+#pragma unroll 4
+		for (unsigned i = 0; i < n2; ++i) {
+			const float4 q = t4[i]; // two points: (x0, h0, x1, h1), broadcast
+#pragma unroll
+			for (int r = 0; r < R; ++r) {
+				const float y0 = fmaf (ca[r], q.x, sa[r] * q.y);
+				const float y1 = fmaf (ca[r], q.z, sa[r] * q.w);
+				pk[r]          = fmaxf (pk[r], fmaxf (fabsf (y0), fabsf (y1)));
+			}
+		}
+		if (n_eval && blockIdx.y == 0 && threadIdx.x == 0) atomicAdd (n_eval, (unsigned long long)cnt);
+	}
+
+#pragma unroll
+	for (int r = 0; r < R; ++r) {
+		const int a = a0 + r * blockDim.x;
+		if (a < A && pk[r] > 0.f) atomicMax (peaks + (long long)c * peaks_stride + a, __float_as_uint (pk[r]));
+	}
+}
+
+// thr2[c] = (min_a peaks[c][a])^2 * (1 - 1e-5): a point whose radius is below
+// that cannot raise any angle's running maximum (|ca x + sa h| <= sqrt(x^2+h^2)
+// up to a few ulp), so dropping it leaves every peak bit-identical.
+// mode 0: keep every point (thr2 = 0); 1: prune; 2: drop every point (no angle wanted)
+__global__ void threshold_kernel (const unsigned* __restrict__ peaks, int peaks_stride, int A, int chan0,
+                                  float* __restrict__ thr2, unsigned* __restrict__ count, int reset_count, int mode)
+{
+	const int c = chan0 + blockIdx.x;
+	if (mode != 1) {
+		if (threadIdx.x == 0) {
+			thr2[c] = mode == 0 ? 0.f : __int_as_float (0x7f800000);
+			if (reset_count) count[c] = 0;
+		}
+		return;
+	}
+	float     m = __int_as_float (0x7f800000);
+	for (int a = threadIdx.x; a < A; a += blockDim.x) {
+		m = fminf (m, __uint_as_float (peaks[(long long)c * peaks_stride + a]));
+	}
+	__shared__ float red[32];
+	for (int o = 16; o; o >>= 1) m = fminf (m, __shfl_xor_sync (0xffffffffu, m, o));
+	if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+	__syncthreads ();
+	if (threadIdx.x < 32) {
+		m = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : __int_as_float (0x7f800000);
+		for (int o = 16; o; o >>= 1) m = fminf (m, __shfl_xor_sync (0xffffffffu, m, o));
+		if (threadIdx.x == 0) {
+			thr2[c] = (m * m) * 0.99999f;
+			if (reset_count) count[c] = 0;
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------
+// Small-call plugin path: direct-form FIR + rotation for n outputs per channel.
+// hist[c] is a linear window of the input stream ending at the newest sample:
+// hist[c][hlen - 1] = x[t_end - 1].  Output u in [u0, u0 + n):
+//   Y[u] = ca_u * x[u - firlat] + sa_u * sum_j g[j] x[u - 1 - 2j]
+// (ca, sa) for output i: pre[c][i] for i < fc.rlen[c], fc.cs[c] after that.
+// ---------------------------------------------------------------------------
+struct FirCoef {
+	float2 cs[2];
+	int    rlen[2];
+};
+__global__ void __launch_bounds__ (128) fir_direct_kernel (const float* __restrict__ hist, int hist_stride, int hlen,
+                                                            long long t_end, long long u0, int n,
+                                                            const float* __restrict__ g, int nodd, int firlat,
+                                                            const float2* __restrict__ pre, int pre_stride, FirCoef fc,
+                                                            float* __restrict__ out, int out_stride)
+{
+	extern __shared__ float sh[]; // g[nodd] then x window
+	const int c   = blockIdx.y;
+	const int o0  = blockIdx.x * blockDim.x; // first output of this CTA (relative)
+	const int nb  = min ((int)blockDim.x, n - o0);
+	if (nb <= 0) return;
+	float* sg = sh;
+	float* sx = sh + nodd;
+	for (int j = threadIdx.x; j < nodd; j += blockDim.x) sg[j] = g[j];
+	// window: x[u_lo - 2 nodd + 1 .. u_hi], u_lo = u0 + o0
+	const long long u_lo = u0 + o0;
+	const int       wlen = 2 * nodd + nb;
+	const long long w0   = u_lo - 2 * nodd; // stream index of sx[0]
+	const float*    hc   = hist + (long long)c * hist_stride;
+	const long long h0   = t_end - hlen;     // stream index of hist[0]
+	for (int i = threadIdx.x; i < wlen; i += blockDim.x) {
+		const long long t = w0 + i;
+		sx[i]             = (t >= h0 && t < t_end && t >= 0) ? hc[t - h0] : 0.f;
+	}
+	__syncthreads ();
+	const int i = threadIdx.x;
+	if (i < nb) {
+		// x[u - 1 - 2j] = sx[(u - w0) - 1 - 2j], u - w0 = 2 nodd + i
+		const float* xp  = sx + 2 * nodd + i - 1;
+		float        a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+		int          j  = 0;
+		for (; j + 3 < nodd; j += 4) {
+			a0 = fmaf (sg[j], xp[-2 * j], a0);
+			a1 = fmaf (sg[j + 1], xp[-2 * j - 2], a1);
+			a2 = fmaf (sg[j + 2], xp[-2 * j - 4], a2);
+			a3 = fmaf (sg[j + 3], xp[-2 * j - 6], a3);
+		}
+		for (; j < nodd; ++j) a0 = fmaf (sg[j], xp[-2 * j], a0);
+		const float  h  = (a0 + a1) + (a2 + a3);
+		const float  xd = sx[2 * nodd + i - firlat];
+		const float2 cs = (o0 + i) < fc.rlen[c] ? pre[(long long)c * pre_stride + o0 + i] : fc.cs[c];
+		out[(long long)c * out_stride + o0 + i] = __fadd_rn (__fmul_rn (cs.x, xd), __fmul_rn (cs.y, h));
+	}
+}
+
+} // namespace prk

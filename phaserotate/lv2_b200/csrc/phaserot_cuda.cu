@@ -1,0 +1,1552 @@
+// libphaserot_cuda: host side of the C ABI declared in include/phaserot_cuda.h.
+//
+// What runs where
+//   host   : FIR design (once), angle tables, the plugin's per-partition angle
+//            ramp state machine, peak-table bookkeeping (PhaseRotate::_peak)
+//   device : everything that touches audio samples (kernels.cuh)
+//
+// There is no CPU fallback in this file: every audio path ends in a kernel
+// launch, and create() refuses to hand out a handle without an sm_100 device.
+#include "../../../include/phaserot_cuda.h"
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <vector>
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+using namespace prk;
+
+namespace {
+
+thread_local char g_last_error[512] = "";
+std::mutex        g_create_lock;
+
+int
+cuda_fail (cudaError_t e, const char* what, int line)
+{
+	snprintf (g_last_error, sizeof (g_last_error), "%s failed at phaserot_cuda.cu:%d: %s", what, line, cudaGetErrorString (e));
+	return PHASEROT_E_CUDA;
+}
+
+#define CK(call)                                              \
+	do {                                                      \
+		cudaError_t e_ = (call);                              \
+		if (e_ != cudaSuccess) {                              \
+			return cuda_fail (e_, #call, __LINE__);           \
+		}                                                     \
+	} while (0)
+
+// ---------------------------------------------------------------------------
+// FIR design (host, once per handle)
+// ---------------------------------------------------------------------------
+
+// Hilbert FIR taps of length L.
+// Reference: cli/phase-rotate.cc:144-161 (window constant 0.5f/L held in float,
+// cli:142) and src/phaserotate.c:374-391 (window constant in double).  Both
+// inverse-transform the half spectrum F[k] = (0, (-1)^k), k = 0..L/2, whose
+// closed form is -2 cot(pi (i - L/2) / L) at odd (i - L/2) and zero elsewhere,
+// then apply a Hann window scaled by 0.5/L in double and store float.
+void
+design_fir (int L, bool plugin, std::vector<float>& taps)
+{
+	taps.assign ((size_t)L, 0.f);
+	const double scale = plugin ? 0.5 / (double)L : (double)(0.5f / (float)L);
+	for (int i = 0; i < L; ++i) {
+		const int m = i - L / 2;
+		if (!(m & 1)) {
+			continue;
+		}
+		const float  raw = (float)(-2.0 / std::tan (M_PI * (double)m / (double)L));
+		const double win = scale * (1.0 - std::cos (2.0 * M_PI * (double)i * (1.0 / (double)L)));
+		taps[(size_t)i]  = (float)((double)raw * win);
+	}
+}
+
+// in-place radix-2 complex FFT (double), n a power of two; sign -1 forward
+void
+host_fft (std::vector<double>& re, std::vector<double>& im, int sign)
+{
+	const size_t n = re.size ();
+	for (size_t i = 1, j = 0; i < n; ++i) {
+		size_t bit = n >> 1;
+		for (; j & bit; bit >>= 1) {
+			j ^= bit;
+		}
+		j ^= bit;
+		if (i < j) {
+			std::swap (re[i], re[j]);
+			std::swap (im[i], im[j]);
+		}
+	}
+	for (size_t len = 2; len <= n; len <<= 1) {
+		const double ang = sign * 2.0 * M_PI / (double)len;
+		for (size_t i = 0; i < n; i += len) {
+			for (size_t k = 0; k < len / 2; ++k) {
+				const double wr = std::cos (ang * (double)k), wi = std::sin (ang * (double)k);
+				const size_t a = i + k, b = i + k + len / 2;
+				const double tr = re[b] * wr - im[b] * wi, ti = re[b] * wi + im[b] * wr;
+				re[b] = re[a] - tr;
+				im[b] = im[a] - ti;
+				re[a] += tr;
+				im[a] += ti;
+			}
+		}
+	}
+}
+
+// reference SinCosLut (cli/phase-rotate.cc:41-72), generalised to subsample S:
+//   float mp = 2.f * M_PI / S / -360.0;  sincosf (mp * i, &s, &c)
+void
+build_lut (int S, std::vector<float>& s, std::vector<float>& c)
+{
+	const int   n  = 180 * S;
+	const float mp = (float)(2.f * M_PI / S / -360.0);
+	s.resize ((size_t)n);
+	c.resize ((size_t)n);
+	for (int i = 0; i < n; ++i) {
+		sincosf (mp * (float)i, &s[(size_t)i], &c[(size_t)i]);
+	}
+}
+
+struct DevBuf {
+	void*  p   = nullptr;
+	size_t cap = 0;
+	int ensure (size_t bytes)
+	{
+		if (bytes <= cap) {
+			return PHASEROT_OK;
+		}
+		if (p) {
+			cudaFree (p);
+			p   = nullptr;
+			cap = 0;
+		}
+		const size_t want = bytes + bytes / 8 + 4096;
+		cudaError_t  e    = cudaMalloc (&p, want);
+		if (e != cudaSuccess) {
+			e = cudaMalloc (&p, bytes);
+			if (e != cudaSuccess) {
+				cudaGetLastError ();
+				snprintf (g_last_error, sizeof (g_last_error), "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString (e));
+				return PHASEROT_E_NOMEM;
+			}
+			cap = bytes;
+			return PHASEROT_OK;
+		}
+		cap = want;
+		return PHASEROT_OK;
+	}
+	void release ()
+	{
+		if (p) {
+			cudaFree (p);
+		}
+		p   = nullptr;
+		cap = 0;
+	}
+};
+
+struct PinBuf {
+	void*  p   = nullptr; // host pointer
+	void*  d   = nullptr; // device alias (mapped)
+	size_t cap = 0;
+	int ensure (size_t bytes)
+	{
+		if (bytes <= cap) {
+			return PHASEROT_OK;
+		}
+		if (p) {
+			cudaFreeHost (p);
+			p = d = nullptr;
+			cap   = 0;
+		}
+		cudaError_t e = cudaHostAlloc (&p, bytes, cudaHostAllocMapped);
+		if (e != cudaSuccess) {
+			cudaGetLastError ();
+			snprintf (g_last_error, sizeof (g_last_error), "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString (e));
+			return PHASEROT_E_NOMEM;
+		}
+		e = cudaHostGetDevicePointer (&d, p, 0);
+		if (e != cudaSuccess) {
+			d = nullptr;
+			cudaGetLastError ();
+		}
+		cap = bytes;
+		return PHASEROT_OK;
+	}
+	void release ()
+	{
+		if (p) {
+			cudaFreeHost (p);
+		}
+		p = d = nullptr;
+		cap   = 0;
+	}
+};
+
+// per-channel angle state of the plugin (Channel::angle/sa/ca, src:53-55)
+struct PluginChan {
+	float               angle = 0.f;
+	float               sa = 0.f, ca = 1.f;
+	std::vector<float2> last;          // coefficients of the last completed partition
+	bool                last_is_ramp = false;
+	float2              last_const   = make_float2 (1.f, 0.f);
+};
+
+} // namespace
+
+struct phaserot {
+	phaserot_cfg_t cfg;
+	int            dev   = 0;
+	int            n_sm  = 148;
+	int            C     = 1;
+	int            L     = 0;   // FIR length
+	int            Lh    = 0;   // half taps
+	int            V     = 0;   // valid complex outputs per segment
+	int            padf  = 0;   // front pad of a plane (complex elements)
+	int            S     = 2;
+	int            MS    = 360; // MAXSAMPLE
+	bool           plugin = false;
+	// plugin sizes (src:278-297)
+	uint32_t P = 0, firlen = 0, firlat = 0;
+
+	cudaStream_t own_stream = nullptr, copy_stream = nullptr, stream = nullptr;
+	cudaEvent_t  ev_copy[2] = { nullptr, nullptr }, ev_done[2] = { nullptr, nullptr };
+
+	std::vector<float> taps, lut_s, lut_c;
+	std::vector<float> table; // [C][MS]  == PhaseRotate::_peak
+
+	DevBuf d_G, d_tw, d_g;
+	DevBuf d_plane, d_out, d_list, d_stage[2], d_io;
+	DevBuf d_small; // count[C] | thr2[C] | raw[C] | ramp_len[C] | stats[2 x u64]
+	DevBuf d_cs, d_peaks, d_ramp, d_chancs;
+	PinBuf h_stage[2], h_res, h_io;
+	long long plane_stride = 0, out_stride = 0, list_stride = 0;
+
+	// pending (asynchronous) sweep result
+	bool             pending = false;
+	std::vector<int> pend_idx;
+	bool             pend_raw = false;
+	int              pend_c0 = 0, pend_c1 = 0;
+	int              pend_A = 0;
+
+	// streaming analyze()
+	std::vector<float> an_buf;
+	int                an_start = 0, an_end = 0, an_stride = 1, an_chn = -1, an_first = 0;
+	uint64_t           an_blocks = 0;
+	std::vector<float> hist; // last L frames of the previous stream (interleaved)
+	bool               hist_valid = false;
+
+	// apply() stream state
+	std::vector<float> ap_hist;
+
+	// plugin stream state
+	std::vector<PluginChan> pch;
+	std::vector<float>      ptail; // [C][firlen + P] newest input last
+	uint64_t                ppos = 0;
+
+	phaserot_stats_t stats {};
+};
+
+namespace {
+
+struct DevGuard {
+	int prev = -1;
+	explicit DevGuard (int dev)
+	{
+		cudaGetDevice (&prev);
+		if (prev != dev) {
+			cudaSetDevice (dev);
+		} else {
+			prev = -1;
+		}
+	}
+	~DevGuard ()
+	{
+		if (prev >= 0) {
+			cudaSetDevice (prev);
+		}
+	}
+};
+
+// d_small: count[64] | thr2[64] | raw[64] | ramp_len[64] | stats[2 x u64]
+constexpr size_t kSmallBytes = 4 * 64 * sizeof (int) + 2 * sizeof (unsigned long long);
+unsigned*           d_count (phaserot* h) { return (unsigned*)h->d_small.p; }
+float*              d_thr2 (phaserot* h) { return (float*)h->d_small.p + 64; }
+unsigned*           d_raw (phaserot* h) { return (unsigned*)h->d_small.p + 128; }
+int*                d_ramplen (phaserot* h) { return (int*)h->d_small.p + 192; }
+unsigned long long* d_stats (phaserot* h) { return (unsigned long long*)((char*)h->d_small.p + 4 * 64 * sizeof (int)); }
+
+int
+upload_tables (phaserot* h)
+{
+	// filter spectrum in the order the forward passes leave it in, scaled by 1/M
+	const int Lh = h->Lh;
+	std::vector<double> re ((size_t)kM, 0.0), im ((size_t)kM, 0.0);
+	for (int j = 0; j < Lh; ++j) {
+		re[(size_t)j] = (double)h->taps[(size_t)(2 * j + 1)];
+	}
+	host_fft (re, im, -1);
+	std::vector<float2> G ((size_t)kM);
+	for (int p = 0; p < kM; ++p) {
+		const int q1 = p >> 10, q2 = (p >> 6) & 15, q3 = (p >> 2) & 15, q4 = p & 3;
+		const int f  = q1 + 16 * q2 + 256 * q3 + 4096 * q4;
+		G[(size_t)p] = make_float2 ((float)(re[(size_t)f] / kM), (float)(im[(size_t)f] / kM));
+	}
+	int rc = h->d_G.ensure (sizeof (float2) * kM);
+	if (rc) return rc;
+	CK (cudaMemcpy (h->d_G.p, G.data (), sizeof (float2) * kM, cudaMemcpyHostToDevice));
+
+	// twiddles W_n^(j q), q in {1,2,3,4,8,12}: [6][1024] | [6][64] | [6][4]
+	static const int qs[6] = { 1, 2, 3, 4, 8, 12 };
+	std::vector<float2> tw;
+	for (int stride : { 1024, 64, 4 }) {
+		const double n = 16.0 * stride;
+		for (int r = 0; r < 6; ++r) {
+			for (int j = 0; j < stride; ++j) {
+				const double a = -2.0 * M_PI * (double)j * qs[r] / n;
+				tw.push_back (make_float2 ((float)std::cos (a), (float)std::sin (a)));
+			}
+		}
+	}
+	rc = h->d_tw.ensure (sizeof (float2) * tw.size ());
+	if (rc) return rc;
+	CK (cudaMemcpy (h->d_tw.p, tw.data (), sizeof (float2) * tw.size (), cudaMemcpyHostToDevice));
+
+	// odd taps for the direct-form small-call path
+	std::vector<float> g ((size_t)Lh);
+	for (int j = 0; j < Lh; ++j) {
+		g[(size_t)j] = h->taps[(size_t)(2 * j + 1)];
+	}
+	rc = h->d_g.ensure (sizeof (float) * (size_t)Lh);
+	if (rc) return rc;
+	CK (cudaMemcpy (h->d_g.p, g.data (), sizeof (float) * (size_t)Lh, cudaMemcpyHostToDevice));
+	return PHASEROT_OK;
+}
+
+void
+fill_conv_common (phaserot* h, ConvParams& p)
+{
+	memset (&p, 0, sizeof (p));
+	p.plane        = (const float2*)h->d_plane.p;
+	p.plane_stride = h->plane_stride;
+	p.padf         = h->padf;
+	p.G            = (const float2*)h->d_G.p;
+	p.tw1          = (const float2*)h->d_tw.p;
+	p.tw2          = p.tw1 + 6 * 1024;
+	p.tw3          = p.tw2 + 6 * 64;
+	p.Lh           = h->Lh;
+	p.V            = h->V;
+}
+
+template <int EPI>
+int
+launch_conv (phaserot* h, const ConvParams& p)
+{
+	static bool attr_done[3] = { false, false, false };
+	if (!attr_done[EPI]) {
+		CK (cudaFuncSetAttribute (fftconv_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+		attr_done[EPI] = true;
+	}
+	const long long total = p.nseg * p.nchan;
+	if (total <= 0) {
+		return PHASEROT_OK;
+	}
+	const int grid = (int)std::min<long long> (total, h->n_sm);
+	fftconv_kernel<EPI><<<grid, kConvThreads, kSmemBytes, h->stream>>> (p);
+	CK (cudaGetLastError ());
+	++h->stats.kernel_launches;
+	return PHASEROT_OK;
+}
+
+// plane geometry for `m_end` complex outputs per channel
+int
+ensure_planes (phaserot* h, long long m_end, long long* nseg_out)
+{
+	const long long nseg   = (m_end + h->V - 1) / h->V;
+	const long long elems  = h->padf + nseg * h->V + 8;
+	const long long stride = (elems + 3) & ~3LL;
+	const int rc = h->d_plane.ensure ((size_t)stride * h->C * sizeof (float2));
+	if (rc) return rc;
+	h->plane_stride = stride;
+	*nseg_out       = nseg;
+	return PHASEROT_OK;
+}
+
+int
+launch_deinterleave (phaserot* h, const float* d_in, long long frame0, long long n_frames_total, long long n_first, long long n_count)
+{
+	if (n_count <= 0) {
+		return PHASEROT_OK;
+	}
+	const int       nt = 256;
+	const long long nb = (n_count + nt - 1) / nt;
+	deinterleave_kernel<<<(unsigned)nb, nt, 0, h->stream>>> (d_in, frame0, n_frames_total, n_first, n_count, h->C,
+	                                                          (float2*)h->d_plane.p, h->plane_stride, h->padf);
+	CK (cudaGetLastError ());
+	++h->stats.kernel_launches;
+	return PHASEROT_OK;
+}
+
+// zero (or fill from `hist_frames`: L frames, interleaved, host) the front pad
+int
+init_front_pad (phaserot* h, const float* hist_frames)
+{
+	for (int c = 0; c < h->C; ++c) {
+		CK (cudaMemsetAsync ((float2*)h->d_plane.p + (long long)c * h->plane_stride, 0, sizeof (float2) * (size_t)h->padf, h->stream));
+	}
+	if (hist_frames) {
+		// history occupies complex indices [-Lh, 0)
+		int rc = h->h_io.ensure (sizeof (float) * (size_t)h->L * h->C);
+		if (rc) return rc;
+		float* st = (float*)h->h_io.p;
+		for (int c = 0; c < h->C; ++c) {
+			for (int i = 0; i < h->L; ++i) {
+				st[(size_t)c * h->L + i] = hist_frames[(size_t)i * h->C + c];
+			}
+			CK (cudaMemcpyAsync ((float2*)h->d_plane.p + (long long)c * h->plane_stride + h->padf - h->Lh, st + (size_t)c * h->L,
+			                     sizeof (float) * (size_t)h->L, cudaMemcpyHostToDevice, h->stream));
+		}
+		CK (cudaStreamSynchronize (h->stream)); // staging buffer is reused
+	}
+	return PHASEROT_OK;
+}
+
+struct SweepCfg {
+	int nt, R, gy;
+};
+SweepCfg
+pick_sweep_cfg (int A)
+{
+	SweepCfg best { 256, 8, (A + 2047) / 2048 };
+	long long best_slots = (long long)best.gy * 2048;
+	for (int R : { 1, 2, 4, 8 }) {
+		for (int nt : { 128, 192, 256 }) {
+			const int per = nt * R;
+			const int gy  = (A + per - 1) / per;
+			if (gy > 1 && R < 8) {
+				continue; // prefer more angles per thread over re-reading the points
+			}
+			const long long slots = (long long)gy * per;
+			if (slots < best_slots || (slots == best_slots && gy < best.gy)) {
+				best       = { nt, R, gy };
+				best_slots = slots;
+			}
+		}
+	}
+	return best;
+}
+
+int
+launch_sweep (phaserot* h, int A, int c0, int nchan)
+{
+	const SweepCfg sc = pick_sweep_cfg (A);
+	int gx = (h->n_sm * 8) / std::max (1, sc.gy * nchan);
+	gx     = std::max (gx, 1);
+	const dim3 grid ((unsigned)gx, (unsigned)sc.gy, (unsigned)nchan);
+	const float2*       lst = (const float2*)h->d_list.p;
+	const float2*       cs  = (const float2*)h->d_cs.p;
+	unsigned*           pk  = (unsigned*)h->d_peaks.p;
+	unsigned long long* ne  = d_stats (h) + 1;
+	switch (sc.R) {
+		case 1: sweep_kernel<1><<<grid, sc.nt, 0, h->stream>>> (lst, h->list_stride, d_count (h), c0, cs, A, pk, h->pend_A, ne); break;
+		case 2: sweep_kernel<2><<<grid, sc.nt, 0, h->stream>>> (lst, h->list_stride, d_count (h), c0, cs, A, pk, h->pend_A, ne); break;
+		case 4: sweep_kernel<4><<<grid, sc.nt, 0, h->stream>>> (lst, h->list_stride, d_count (h), c0, cs, A, pk, h->pend_A, ne); break;
+		default: sweep_kernel<8><<<grid, sc.nt, 0, h->stream>>> (lst, h->list_stride, d_count (h), c0, cs, A, pk, h->pend_A, ne); break;
+	}
+	CK (cudaGetLastError ());
+	++h->stats.kernel_launches;
+	return PHASEROT_OK;
+}
+
+// merge a finished device sweep into the host table (PhaseRotate::_peak semantics: running max)
+int
+finish_pending (phaserot* h)
+{
+	if (!h->pending) {
+		return PHASEROT_OK;
+	}
+	const int    A     = h->pend_A;
+	const size_t bytes = sizeof (unsigned) * ((size_t)A * h->C + (size_t)h->C) + 2 * sizeof (unsigned long long);
+	int          rc    = h->h_res.ensure (bytes);
+	if (rc) return rc;
+	unsigned* res = (unsigned*)h->h_res.p;
+	if (A > 0) {
+		CK (cudaMemcpyAsync (res, h->d_peaks.p, sizeof (unsigned) * (size_t)A * h->C, cudaMemcpyDeviceToHost, h->stream));
+	}
+	CK (cudaMemcpyAsync (res + (size_t)A * h->C, d_raw (h), sizeof (unsigned) * (size_t)h->C, cudaMemcpyDeviceToHost, h->stream));
+	unsigned long long* st = (unsigned long long*)(res + (size_t)A * h->C + (size_t)h->C + (((size_t)A * h->C + h->C) & 1));
+	CK (cudaMemcpyAsync (st, d_stats (h), 2 * sizeof (unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+	CK (cudaStreamSynchronize (h->stream));
+	h->stats.d2h_bytes += bytes;
+	for (int c = h->pend_c0; c < h->pend_c1; ++c) {
+		float* row = h->table.data () + (size_t)c * h->MS;
+		for (int k = 0; k < A; ++k) {
+			float v;
+			memcpy (&v, &res[(size_t)c * A + k], sizeof (float));
+			const int a = h->pend_idx[(size_t)k];
+			row[a]      = std::max (row[a], v);
+		}
+		if (h->pend_raw) {
+			float v;
+			memcpy (&v, &res[(size_t)A * h->C + c], sizeof (float));
+			row[0] = std::max (row[0], v);
+		}
+	}
+	h->stats.points_total += st[0];
+	h->stats.points_evaluated += st[1];
+	h->pending = false;
+	return PHASEROT_OK;
+}
+
+// The angle loop of PhaseRotate::thr_process (cli/phase-rotate.cc:409-428).
+int
+angle_schedule (phaserot* h, int ang_start, int ang_end, int ang_stride, std::vector<int>& idx, bool& raw)
+{
+	if (ang_stride < 1) {
+		return PHASEROT_E_INVAL;
+	}
+	std::vector<char> seen ((size_t)h->MS, 0);
+	idx.clear ();
+	raw       = false;
+	int angle = ang_start;
+	while (angle <= ang_end) {
+		if (angle == 0) {
+			raw = true; // cli:413-414: raw input peak
+		} else {
+			const int a = ((angle % h->MS) + h->MS) % h->MS;
+			if (!seen[(size_t)a]) {
+				seen[(size_t)a] = 1;
+				idx.push_back (a);
+			}
+		}
+		angle += ang_stride;
+		if (angle >= ang_end) {
+			break;
+		}
+	}
+	return PHASEROT_OK;
+}
+
+/*
+ * One analysis pass over a stream.
+ *   src          interleaved frames (host or device)
+ *   n_frames     frames present in src
+ *   t_end        the pass examines output samples t in [0, t_end)
+ *   first_block  apply the first-block rule (cli:418-419) to t < L
+ *   hist         L frames of history preceding src (host, interleaved) or null
+ */
+int
+sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frames, long long t_end, bool first_block,
+            const float* hist, int ang_start, int ang_end, int ang_stride, int chn)
+{
+	if (chn >= h->C) {
+		return PHASEROT_E_INVAL;
+	}
+	int rc = finish_pending (h);
+	if (rc) return rc;
+
+	std::vector<int> idx;
+	bool             raw = false;
+	rc                   = angle_schedule (h, ang_start, ang_end, ang_stride, idx, raw);
+	if (rc) return rc;
+	const int A  = (int)idx.size ();
+	const int c0 = chn < 0 ? 0 : chn;
+	const int c1 = chn < 0 ? h->C : chn + 1;
+
+	// angle table
+	std::vector<float2> cs ((size_t)std::max (A, 1));
+	for (int k = 0; k < A; ++k) {
+		cs[(size_t)k] = make_float2 (h->lut_c[(size_t)idx[(size_t)k]], h->lut_s[(size_t)idx[(size_t)k]]);
+	}
+	rc = h->d_cs.ensure (sizeof (float2) * cs.size ());
+	if (rc) return rc;
+	rc = h->d_peaks.ensure (sizeof (unsigned) * (size_t)std::max (A, 1) * h->C);
+	if (rc) return rc;
+	CK (cudaMemcpyAsync (h->d_cs.p, cs.data (), sizeof (float2) * cs.size (), cudaMemcpyHostToDevice, h->stream));
+	CK (cudaStreamSynchronize (h->stream)); // cs is a stack-lifetime buffer
+	CK (cudaMemsetAsync (h->d_peaks.p, 0, sizeof (unsigned) * (size_t)std::max (A, 1) * h->C, h->stream));
+	CK (cudaMemsetAsync (h->d_small.p, 0, kSmallBytes, h->stream));
+
+	const long long m_end = (t_end + 1) / 2;
+	long long       nseg  = 0;
+	rc                    = ensure_planes (h, m_end, &nseg);
+	if (rc) return rc;
+	rc = init_front_pad (h, hist);
+	if (rc) return rc;
+
+	// survivor list: one launch covers at most `segs_max` segments per channel
+	const int       nchan    = c1 - c0;
+	const long long segs_max = std::max<long long> (1, ((long long)h->n_sm * 8) / nchan);
+	h->list_stride           = std::min (segs_max, std::max<long long> (nseg, 1)) * h->V * 2;
+	rc                       = h->d_list.ensure ((size_t)h->list_stride * h->C * sizeof (float2));
+	if (rc) return rc;
+
+	h->pend_idx = idx;
+	h->pend_raw = raw;
+	h->pend_c0  = c0;
+	h->pend_c1  = c1;
+	h->pend_A   = A;
+
+	ConvParams p;
+	fill_conv_common (h, p);
+	p.chan0  = c0;
+	p.nchan  = nchan;
+	p.m_end  = m_end;
+	p.m_skip = (first_block && !(h->cfg.flags & PHASEROT_FLAG_NO_FIRST_BLOCK_QUIRK)) ? h->Lh / 2 : 0;
+	p.m_zero = (first_block && !(h->cfg.flags & PHASEROT_FLAG_NO_FIRST_BLOCK_QUIRK)) ? h->Lh : 0;
+	p.list        = (float2*)h->d_list.p;
+	p.list_stride = h->list_stride;
+	p.count       = d_count (h);
+	p.thr2        = d_thr2 (h);
+	p.rawpeak     = d_raw (h);
+	p.n_seen      = d_stats (h);
+	const int thr_mode = A == 0 ? 2 : (h->cfg.flags & PHASEROT_FLAG_NO_PRUNE) ? 0 : 1;
+	threshold_kernel<<<nchan, 32, 0, h->stream>>> ((const unsigned*)h->d_peaks.p, A, A, c0, d_thr2 (h), d_count (h), 1, A == 0 ? 2 : 0);
+	CK (cudaGetLastError ());
+	++h->stats.kernel_launches;
+
+	// complex elements that must be filled: up to nseg * V (zero beyond the data)
+	const long long n_fill  = nseg * h->V;
+	const long long n_data  = (n_frames + 1) / 2; // complex elements that hold data
+	long long       filled  = 0;                  // complex elements deinterleaved so far
+	long long       seg_done = 0;
+	long long       launch_segs = std::max<long long> (1, (h->n_sm + nchan - 1) / nchan);
+
+	auto process_ready = [&] (bool final) -> int {
+		const long long seg_ready = final ? nseg : std::min (nseg, filled / h->V);
+		while (seg_done < seg_ready) {
+			long long n = std::min (launch_segs, seg_ready - seg_done);
+			if (!final && n < launch_segs && seg_ready < nseg) {
+				break; // wait for more data to keep launches full
+			}
+			p.seg0 = seg_done;
+			p.nseg = n;
+			int r  = launch_conv<EPI_POINTS> (h, p);
+			if (r) return r;
+			if (A > 0) {
+				r = launch_sweep (h, A, c0, nchan);
+				if (r) return r;
+			}
+			threshold_kernel<<<nchan, 256, 0, h->stream>>> ((const unsigned*)h->d_peaks.p, A, A, c0, d_thr2 (h), d_count (h), 1, thr_mode);
+			CK (cudaGetLastError ());
+			++h->stats.kernel_launches;
+			seg_done += n;
+			launch_segs = std::min (segs_max, launch_segs * 2);
+		}
+		return PHASEROT_OK;
+	};
+
+	if (src_is_device) {
+		rc = launch_deinterleave (h, src, 0, n_frames, 0, n_fill);
+		if (rc) return rc;
+		filled = n_fill;
+		rc     = process_ready (true);
+		if (rc) return rc;
+	} else {
+		// double-buffered H2D on the copy stream, compute on the main stream
+		const long long chunk_frames = std::max<long long> (2, ((8LL << 20) / h->C) & ~1LL); // ~32 MB per chunk
+		for (int b = 0; b < 2; ++b) {
+			rc = h->d_stage[b].ensure (sizeof (float) * (size_t)chunk_frames * h->C);
+			if (rc) return rc;
+		}
+		cudaPointerAttributes at;
+		bool pinned = (cudaPointerGetAttributes (&at, src) == cudaSuccess) && (at.type == cudaMemoryTypeHost);
+		cudaGetLastError ();
+		if (!pinned) {
+			for (int b = 0; b < 2; ++b) {
+				rc = h->h_stage[b].ensure (sizeof (float) * (size_t)chunk_frames * h->C);
+				if (rc) return rc;
+			}
+		}
+		int       b  = 0;
+		long long f0 = 0;
+		bool      used[2] = { false, false };
+		while (f0 < n_frames) {
+			const long long nf    = std::min (chunk_frames, n_frames - f0);
+			const size_t    bytes = sizeof (float) * (size_t)nf * h->C;
+			if (used[b]) {
+				CK (cudaStreamWaitEvent (h->copy_stream, h->ev_done[b], 0)); // staging buffer free again
+			}
+			const float* hsrc = src + (size_t)f0 * h->C;
+			if (!pinned) {
+				if (used[b]) {
+					CK (cudaEventSynchronize (h->ev_copy[b]));
+				}
+				memcpy (h->h_stage[b].p, hsrc, bytes);
+				hsrc = (const float*)h->h_stage[b].p;
+			}
+			CK (cudaMemcpyAsync (h->d_stage[b].p, hsrc, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+			CK (cudaEventRecord (h->ev_copy[b], h->copy_stream));
+			CK (cudaStreamWaitEvent (h->stream, h->ev_copy[b], 0));
+			h->stats.h2d_bytes += bytes;
+			const long long n_first = f0 / 2;
+			const long long n_cnt   = (f0 + nf + 1) / 2 - n_first;
+			rc = launch_deinterleave (h, (const float*)h->d_stage[b].p, f0, n_frames, n_first, n_cnt);
+			if (rc) return rc;
+			CK (cudaEventRecord (h->ev_done[b], h->stream));
+			used[b] = true;
+			filled  = n_first + n_cnt;
+			f0 += nf;
+			if (f0 < n_frames) {
+				// only whole elements strictly inside the data are final
+				filled = f0 / 2;
+				rc     = process_ready (false);
+				if (rc) return rc;
+			}
+			b ^= 1;
+		}
+		// zero tail beyond the data
+		if (n_fill > n_data) {
+			for (int c = 0; c < h->C; ++c) {
+				CK (cudaMemsetAsync ((float2*)h->d_plane.p + (long long)c * h->plane_stride + h->padf + n_data, 0,
+				                     sizeof (float2) * (size_t)(n_fill - n_data), h->stream));
+			}
+		}
+		rc = process_ready (true);
+		if (rc) return rc;
+	}
+	h->pending = true;
+	return PHASEROT_OK;
+}
+
+/*
+ * Render stream: y[t] = ca x[t - L/2] + sa H[t] for t in [0, t_end), planar
+ * result left in d_out (float2 per two samples).
+ */
+int
+render_core (phaserot* h, const float* src, bool src_is_device, long long n_frames, long long t_end, const float* hist,
+             const float2* chan_cs /*host [C]*/, const float2* ramp /*host [C][ramp_stride] or null*/, long long ramp_stride,
+             const int* ramp_len /*host [C] or null*/, long long* m_end_out)
+{
+	const long long m_end = (t_end + 1) / 2;
+	long long       nseg  = 0;
+	int             rc    = ensure_planes (h, m_end, &nseg);
+	if (rc) return rc;
+	rc = init_front_pad (h, hist);
+	if (rc) return rc;
+	h->out_stride = (m_end + 3) & ~3LL;
+	rc            = h->d_out.ensure (sizeof (float2) * (size_t)h->out_stride * h->C);
+	if (rc) return rc;
+	rc = h->d_chancs.ensure (sizeof (float2) * (size_t)h->C);
+	if (rc) return rc;
+	CK (cudaMemcpyAsync (h->d_chancs.p, chan_cs, sizeof (float2) * (size_t)h->C, cudaMemcpyHostToDevice, h->stream));
+	if (ramp && ramp_len) {
+		rc = h->d_ramp.ensure (sizeof (float2) * (size_t)ramp_stride * h->C);
+		if (rc) return rc;
+		CK (cudaMemcpyAsync (h->d_ramp.p, ramp, sizeof (float2) * (size_t)ramp_stride * h->C, cudaMemcpyHostToDevice, h->stream));
+		CK (cudaMemcpyAsync (d_ramplen (h), ramp_len, sizeof (int) * (size_t)h->C, cudaMemcpyHostToDevice, h->stream));
+	}
+	CK (cudaStreamSynchronize (h->stream)); // small host arrays above may be stack buffers
+
+	const long long n_fill = nseg * h->V;
+	if (src_is_device) {
+		rc = launch_deinterleave (h, src, 0, n_frames, 0, n_fill);
+		if (rc) return rc;
+	} else {
+		const size_t bytes = sizeof (float) * (size_t)n_frames * h->C;
+		rc                 = h->d_io.ensure (std::max<size_t> (bytes, 16));
+		if (rc) return rc;
+		if (bytes) {
+			CK (cudaMemcpyAsync (h->d_io.p, src, bytes, cudaMemcpyHostToDevice, h->stream));
+			h->stats.h2d_bytes += bytes;
+		}
+		rc = launch_deinterleave (h, (const float*)h->d_io.p, 0, n_frames, 0, n_fill);
+		if (rc) return rc;
+	}
+	ConvParams p;
+	fill_conv_common (h, p);
+	p.chan0       = 0;
+	p.nchan       = h->C;
+	p.seg0        = 0;
+	p.nseg        = nseg;
+	p.m_end       = m_end;
+	p.out         = (float2*)h->d_out.p;
+	p.out_stride  = h->out_stride;
+	p.cs          = (const float2*)h->d_chancs.p;
+	p.ramp        = (ramp && ramp_len) ? (const float2*)h->d_ramp.p : nullptr;
+	p.ramp_stride = ramp_stride;
+	p.ramp_len    = (ramp && ramp_len) ? d_ramplen (h) : nullptr;
+	rc            = launch_conv<EPI_RENDER> (h, p);
+	if (rc) return rc;
+	*m_end_out = m_end;
+	return PHASEROT_OK;
+}
+
+int
+launch_interleave (phaserot* h, long long m_count, long long m_first, float* d_dst, long long n_frames_out)
+{
+	if (m_count <= 0) {
+		return PHASEROT_OK;
+	}
+	const int       nt = 256;
+	const long long nb = (m_count + nt - 1) / nt;
+	interleave_kernel<<<(unsigned)nb, nt, 0, h->stream>>> ((const float2*)h->d_out.p + m_first, h->out_stride, h->C, m_count, d_dst, n_frames_out);
+	CK (cudaGetLastError ());
+	++h->stats.kernel_launches;
+	return PHASEROT_OK;
+}
+
+int
+flush_analyze (phaserot* h)
+{
+	if (h->an_blocks == 0) {
+		return PHASEROT_OK;
+	}
+	const long long frames = (long long)h->an_blocks * h->L;
+	const int rc = sweep_core (h, h->an_buf.data (), false, frames, frames, h->an_first != 0, h->hist_valid ? h->hist.data () : nullptr,
+	                           h->an_start, h->an_end, h->an_stride, h->an_chn);
+	if (rc) return rc;
+	// keep the last block as history for a continued stream
+	h->hist.assign (h->an_buf.end () - (size_t)h->L * h->C, h->an_buf.end ());
+	h->hist_valid = true;
+	h->an_buf.clear ();
+	h->an_blocks = 0;
+	h->an_first  = 0;
+	return finish_pending (h);
+}
+
+// src/phaserotate.c:122-133
+inline void
+plugin_sin_cos (float angle, float* s, float* c)
+{
+	static const float twopi = (float)(2 * M_PI);
+	sincosf (angle * twopi, s, c);
+}
+
+/*
+ * Angle handling of one completed partition (src/phaserotate.c:673-717):
+ * fills coef[0..P) with the (ca, sa) used for each sample and updates the
+ * channel's angle state.  Returns true when the partition was ramped.
+ */
+bool
+plugin_partition_coef (phaserot* h, PluginChan& ch, float target, float2* coef)
+{
+	const uint32_t P = h->P;
+	if (target != ch.angle) {
+		const float interp_nm = 1.f / (float)P;    // src:296
+		const float thresh    = (float)P * 1e-6f;  // src:295
+		float       da        = target - ch.angle;
+		if (fabs (da) > 0.5) { // wrap around at +/- 180 (src:676-683)
+			if (da < 0) {
+				da += 1.f;
+			} else {
+				da -= 1.f;
+			}
+		}
+		da *= interp_nm;
+		bool final = false;
+		if (da > thresh) {
+			da = thresh;
+		} else if (da < -thresh) {
+			da = -thresh;
+		} else {
+			final = true;
+		}
+		float angle = ch.angle;
+		for (uint32_t i = 0; i < P; ++i) {
+			float s, c;
+			plugin_sin_cos (angle, &s, &c);
+			coef[i] = make_float2 (c, s);
+			angle += da;
+		}
+		if (final) {
+			angle = target;
+		}
+		ch.angle = angle;
+		if (angle == target) {
+			plugin_sin_cos (angle, &ch.sa, &ch.ca);
+		}
+		return true;
+	}
+	for (uint32_t i = 0; i < P; ++i) {
+		coef[i] = make_float2 (ch.ca, ch.sa);
+	}
+	return false;
+}
+
+} // namespace
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+
+extern "C" {
+
+int
+phaserot_abi_version (void)
+{
+	return PHASEROT_ABI_VERSION;
+}
+
+const char*
+phaserot_strerror (int code)
+{
+	switch (code) {
+		case PHASEROT_OK: return "ok";
+		case PHASEROT_E_INVAL: return "invalid argument";
+		case PHASEROT_E_NO_DEVICE: return "no usable sm_100 CUDA device (this backend has no CPU fallback)";
+		case PHASEROT_E_CUDA: return "CUDA error";
+		case PHASEROT_E_NOMEM: return "out of memory";
+		case PHASEROT_E_UNSUPPORTED: return "configuration not supported by the device path";
+		case PHASEROT_E_STATE: return "call not valid in this mode";
+		default: return "unknown error";
+	}
+}
+
+const char*
+phaserot_last_error (void)
+{
+	return g_last_error;
+}
+
+int
+phaserot_create (phaserot_t** out, const phaserot_cfg_t* cfg)
+{
+	if (!out) {
+		return PHASEROT_E_INVAL;
+	}
+	*out = nullptr;
+	if (!cfg || cfg->abi_version != PHASEROT_ABI_VERSION) {
+		return PHASEROT_E_INVAL;
+	}
+	const bool plugin = cfg->mode == PHASEROT_MODE_PLUGIN;
+	if (cfg->mode != PHASEROT_MODE_CLI && !plugin) {
+		return PHASEROT_E_INVAL;
+	}
+	if (cfg->n_channels < 1 || cfg->n_channels > 64 || (plugin && cfg->n_channels > 2)) {
+		return PHASEROT_E_INVAL;
+	}
+	int L = 0;
+	uint32_t P = 0, firlen = 0;
+	if (plugin) {
+		if (!(cfg->sample_rate > 0)) {
+			return PHASEROT_E_INVAL;
+		}
+		// src/phaserotate.c:278-297
+		uint32_t fftlen;
+		if (cfg->sample_rate < 64000) {
+			fftlen = 512;
+			firlen = 3072;
+		} else if (cfg->sample_rate < 128000) {
+			fftlen = 1024;
+			firlen = 4096;
+		} else {
+			fftlen = 2048;
+			firlen = 8192;
+		}
+		P = fftlen / 2;
+		L = (int)firlen;
+	} else {
+		L = cfg->blksiz;
+		// cli/phase-rotate.cc:749-755: power of two in [1024, 32768]
+		if (L < 1024 || L > 32768 || (L & (L - 1))) {
+			return PHASEROT_E_INVAL;
+		}
+	}
+	const int S = cfg->subsample == 0 ? 2 : cfg->subsample;
+	if (S < 1 || S > 1000) {
+		return PHASEROT_E_INVAL;
+	}
+	if (L / 2 > kM / 2) {
+		snprintf (g_last_error, sizeof (g_last_error), "FIR length %d needs %d half-taps; this build supports at most %d", L, L / 2, kM / 2);
+		return PHASEROT_E_UNSUPPORTED;
+	}
+
+	std::lock_guard<std::mutex> lk (g_create_lock);
+
+	int ndev = 0;
+	if (cudaGetDeviceCount (&ndev) != cudaSuccess || ndev < 1) {
+		cudaGetLastError ();
+		snprintf (g_last_error, sizeof (g_last_error), "no CUDA device");
+		return PHASEROT_E_NO_DEVICE;
+	}
+	int dev = cfg->device;
+	if (dev < 0) {
+		if (cudaGetDevice (&dev) != cudaSuccess) {
+			dev = 0;
+		}
+	}
+	if (dev >= ndev) {
+		return PHASEROT_E_INVAL;
+	}
+	cudaDeviceProp prop;
+	if (cudaGetDeviceProperties (&prop, dev) != cudaSuccess) {
+		cudaGetLastError ();
+		return PHASEROT_E_NO_DEVICE;
+	}
+	if (prop.major != 10) {
+		snprintf (g_last_error, sizeof (g_last_error), "device %d is sm_%d%d; this library contains sm_100a code only", dev, prop.major, prop.minor);
+		return PHASEROT_E_NO_DEVICE;
+	}
+
+	phaserot* h = new (std::nothrow) phaserot ();
+	if (!h) {
+		return PHASEROT_E_NOMEM;
+	}
+	h->cfg    = *cfg;
+	h->dev    = dev;
+	h->n_sm   = prop.multiProcessorCount;
+	h->C      = cfg->n_channels;
+	h->L      = L;
+	h->Lh     = L / 2;
+	h->V      = kM - h->Lh;
+	h->padf   = (h->Lh + 3) & ~3;
+	h->S      = S;
+	h->MS     = 180 * S;
+	h->plugin = plugin;
+	h->P      = P;
+	h->firlen = firlen;
+	h->firlat = firlen / 2;
+
+	DevGuard guard (dev);
+	int      rc = PHASEROT_OK;
+	do {
+		design_fir (L, plugin, h->taps);
+		build_lut (S, h->lut_s, h->lut_c);
+		h->table.assign ((size_t)h->C * h->MS, 0.f);
+		cudaError_t e = cudaStreamCreateWithFlags (&h->own_stream, cudaStreamNonBlocking);
+		if (e == cudaSuccess) e = cudaStreamCreateWithFlags (&h->copy_stream, cudaStreamNonBlocking);
+		for (int b = 0; b < 2 && e == cudaSuccess; ++b) {
+			e = cudaEventCreateWithFlags (&h->ev_copy[b], cudaEventDisableTiming);
+			if (e == cudaSuccess) e = cudaEventCreateWithFlags (&h->ev_done[b], cudaEventDisableTiming);
+		}
+		if (e != cudaSuccess) {
+			rc = cuda_fail (e, "stream/event creation", __LINE__);
+			break;
+		}
+		h->stream = h->own_stream;
+		rc        = h->d_small.ensure (kSmallBytes);
+		if (rc) break;
+		if (cudaMemset (h->d_small.p, 0, kSmallBytes) != cudaSuccess) {
+			rc = PHASEROT_E_CUDA;
+			break;
+		}
+		rc = upload_tables (h);
+		if (rc) break;
+		if (plugin) {
+			h->pch.resize ((size_t)h->C);
+			for (auto& ch : h->pch) {
+				ch.last.assign (P, make_float2 (1.f, 0.f));
+				plugin_sin_cos (0.f, &ch.sa, &ch.ca); // channel_init, src:147,159
+				ch.last_const = make_float2 (ch.ca, ch.sa);
+			}
+			h->ptail.assign ((size_t)h->C * (firlen + P), 0.f);
+		} else {
+			h->ap_hist.assign ((size_t)h->C * L, 0.f);
+		}
+	} while (0);
+	if (rc) {
+		phaserot_destroy (h);
+		return rc;
+	}
+	*out = h;
+	return PHASEROT_OK;
+}
+
+void
+phaserot_destroy (phaserot_t* h)
+{
+	if (!h) {
+		return;
+	}
+	std::lock_guard<std::mutex> lk (g_create_lock);
+	DevGuard                    guard (h->dev);
+	if (h->own_stream) cudaStreamSynchronize (h->own_stream);
+	if (h->copy_stream) cudaStreamSynchronize (h->copy_stream);
+	for (DevBuf* b : { &h->d_G, &h->d_tw, &h->d_g, &h->d_plane, &h->d_out, &h->d_list, &h->d_stage[0], &h->d_stage[1], &h->d_io, &h->d_small,
+	                   &h->d_cs, &h->d_peaks, &h->d_ramp, &h->d_chancs }) {
+		b->release ();
+	}
+	for (PinBuf* b : { &h->h_stage[0], &h->h_stage[1], &h->h_res, &h->h_io }) {
+		b->release ();
+	}
+	for (int b = 0; b < 2; ++b) {
+		if (h->ev_copy[b]) cudaEventDestroy (h->ev_copy[b]);
+		if (h->ev_done[b]) cudaEventDestroy (h->ev_done[b]);
+	}
+	if (h->own_stream) cudaStreamDestroy (h->own_stream);
+	if (h->copy_stream) cudaStreamDestroy (h->copy_stream);
+	delete h;
+}
+
+int
+phaserot_set_stream (phaserot_t* h, void* cuda_stream)
+{
+	if (!h) {
+		return PHASEROT_E_INVAL;
+	}
+	DevGuard guard (h->dev);
+	const int rc = finish_pending (h);
+	if (rc) return rc;
+	h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+	return PHASEROT_OK;
+}
+
+int
+phaserot_reset (phaserot_t* h)
+{
+	if (!h) {
+		return PHASEROT_E_INVAL;
+	}
+	DevGuard guard (h->dev);
+	CK (cudaStreamSynchronize (h->stream));
+	h->pending = false;
+	std::fill (h->table.begin (), h->table.end (), 0.f);
+	h->an_buf.clear ();
+	h->an_blocks  = 0;
+	h->an_first   = 0;
+	h->hist_valid = false;
+	std::fill (h->ap_hist.begin (), h->ap_hist.end (), 0.f);
+	if (h->plugin) {
+		// activate() clears buffers but keeps the angle state (src:169-177, 511-520)
+		std::fill (h->ptail.begin (), h->ptail.end (), 0.f);
+		h->ppos = 0;
+		for (auto& ch : h->pch) {
+			ch.last_is_ramp = false;
+			ch.last_const   = make_float2 (ch.ca, ch.sa);
+		}
+	}
+	return PHASEROT_OK;
+}
+
+int
+phaserot_sweep (phaserot_t* h, const float* interleaved, uint64_t n_frames, int ang_start, int ang_end, int ang_stride, int chn)
+{
+	if (!h || (!interleaved && n_frames)) {
+		return PHASEROT_E_INVAL;
+	}
+	if (h->plugin) {
+		return PHASEROT_E_STATE;
+	}
+	DevGuard        guard (h->dev);
+	const long long F = (long long)n_frames;
+	const long long B = (F + h->L - 1) / h->L;
+	// analyze_file: B real blocks + one zero flush block (cli:572-586)
+	int rc = sweep_core (h, interleaved, false, F, (B + 1) * h->L, B > 0, nullptr, ang_start, ang_end, ang_stride, chn);
+	if (rc) return rc;
+	return finish_pending (h);
+}
+
+int
+phaserot_sweep_device (phaserot_t* h, const float* d_interleaved, uint64_t n_frames, int ang_start, int ang_end, int ang_stride, int chn)
+{
+	if (!h || (!d_interleaved && n_frames)) {
+		return PHASEROT_E_INVAL;
+	}
+	if (h->plugin) {
+		return PHASEROT_E_STATE;
+	}
+	DevGuard        guard (h->dev);
+	const long long F = (long long)n_frames;
+	const long long B = (F + h->L - 1) / h->L;
+	return sweep_core (h, d_interleaved, true, F, (B + 1) * h->L, B > 0, nullptr, ang_start, ang_end, ang_stride, chn);
+}
+
+int
+phaserot_analyze (phaserot_t* h, const float* block, int ang_start, int ang_end, int ang_stride, int chn, int start)
+{
+	if (!h || !block) {
+		return PHASEROT_E_INVAL;
+	}
+	if (h->plugin) {
+		return PHASEROT_E_STATE;
+	}
+	DevGuard guard (h->dev);
+	if (h->an_blocks && (ang_start != h->an_start || ang_end != h->an_end || ang_stride != h->an_stride || chn != h->an_chn)) {
+		const int rc = flush_analyze (h);
+		if (rc) return rc;
+	}
+	if (h->an_blocks == 0) {
+		h->an_start  = ang_start;
+		h->an_end    = ang_end;
+		h->an_stride = ang_stride;
+		h->an_chn    = chn;
+		h->an_first  = start;
+		if (start) {
+			h->hist_valid = false;
+		}
+	}
+	try {
+		h->an_buf.insert (h->an_buf.end (), block, block + (size_t)h->L * h->C);
+	} catch (...) {
+		return PHASEROT_E_NOMEM;
+	}
+	++h->an_blocks;
+	// bound the staging memory: flush every ~256 MB
+	if (h->an_buf.size () * sizeof (float) >= (256u << 20)) {
+		return flush_analyze (h);
+	}
+	return PHASEROT_OK;
+}
+
+int
+phaserot_sync (phaserot_t* h)
+{
+	if (!h) {
+		return PHASEROT_E_INVAL;
+	}
+	DevGuard guard (h->dev);
+	int      rc = flush_analyze (h);
+	if (rc) return rc;
+	rc = finish_pending (h);
+	if (rc) return rc;
+	CK (cudaStreamSynchronize (h->stream));
+	return PHASEROT_OK;
+}
+
+float
+phaserot_peak (phaserot_t* h, int c, int a)
+{
+	if (!h || phaserot_sync (h) != PHASEROT_OK) {
+		return NAN;
+	}
+	a = ((a % h->MS) + h->MS) % h->MS;
+	if (c < 0 || c >= h->C) {
+		// PhaseRotate::peak_all (cli:287-299)
+		float p = 0;
+		for (int k = 0; k < h->C; ++k) {
+			p = std::max (p, h->table[(size_t)k * h->MS + a]);
+		}
+		return p;
+	}
+	return h->table[(size_t)c * h->MS + a];
+}
+
+int
+phaserot_peaks (phaserot_t* h, float* out)
+{
+	if (!h || !out) {
+		return PHASEROT_E_INVAL;
+	}
+	const int rc = phaserot_sync (h);
+	if (rc) return rc;
+	memcpy (out, h->table.data (), sizeof (float) * h->table.size ());
+	return PHASEROT_OK;
+}
+
+int
+phaserot_lut (phaserot_t* h, float* s, float* c)
+{
+	if (!h || !s || !c) {
+		return PHASEROT_E_INVAL;
+	}
+	memcpy (s, h->lut_s.data (), sizeof (float) * (size_t)h->MS);
+	memcpy (c, h->lut_c.data (), sizeof (float) * (size_t)h->MS);
+	return PHASEROT_OK;
+}
+
+static int
+angles_to_cs (phaserot* h, const int* angles, std::vector<float2>& cs)
+{
+	cs.resize ((size_t)h->C);
+	for (int c = 0; c < h->C; ++c) {
+		const int a   = ((angles[c] % h->MS) + h->MS) % h->MS; // cli:463
+		cs[(size_t)c] = make_float2 (h->lut_c[(size_t)a], h->lut_s[(size_t)a]);
+	}
+	return PHASEROT_OK;
+}
+
+int
+phaserot_apply (phaserot_t* h, float* buf, const int* angles)
+{
+	if (!h || !buf || !angles) {
+		return PHASEROT_E_INVAL;
+	}
+	if (h->plugin) {
+		return PHASEROT_E_STATE;
+	}
+	DevGuard            guard (h->dev);
+	std::vector<float2> cs;
+	angles_to_cs (h, angles, cs);
+	long long m_end = 0;
+	int       rc    = render_core (h, buf, false, h->L, h->L, h->ap_hist.data (), cs.data (), nullptr, 0, nullptr, &m_end);
+	if (rc) return rc;
+	// remember the input block as history (cli:461) before it is overwritten
+	memcpy (h->ap_hist.data (), buf, sizeof (float) * (size_t)h->L * h->C);
+	rc = h->d_io.ensure (sizeof (float) * (size_t)h->L * h->C);
+	if (rc) return rc;
+	rc = launch_interleave (h, m_end, 0, (float*)h->d_io.p, h->L);
+	if (rc) return rc;
+	CK (cudaMemcpyAsync (buf, h->d_io.p, sizeof (float) * (size_t)h->L * h->C, cudaMemcpyDeviceToHost, h->stream));
+	CK (cudaStreamSynchronize (h->stream));
+	h->stats.d2h_bytes += sizeof (float) * (size_t)h->L * h->C;
+	return PHASEROT_OK;
+}
+
+static int
+render_bulk (phaserot* h, const float* src, bool dev_in, uint64_t n_frames, const int* angles, int flush_blocks, float* dst, bool dev_out)
+{
+	if (!h || (!src && n_frames) || !angles || !dst || flush_blocks < 0) {
+		return PHASEROT_E_INVAL;
+	}
+	if (h->plugin) {
+		return PHASEROT_E_STATE;
+	}
+	DevGuard            guard (h->dev);
+	std::vector<float2> cs;
+	angles_to_cs (h, angles, cs);
+	const long long F     = (long long)n_frames;
+	const long long B     = (F + h->L - 1) / h->L;
+	const long long t_end = (B + flush_blocks) * h->L;
+	if (t_end == 0) {
+		return PHASEROT_OK;
+	}
+	long long m_end = 0;
+	int       rc    = render_core (h, src, dev_in, F, t_end, nullptr, cs.data (), nullptr, 0, nullptr, &m_end);
+	if (rc) return rc;
+	if (dev_out) {
+		return launch_interleave (h, m_end, 0, dst, t_end);
+	}
+	const size_t bytes = sizeof (float) * (size_t)t_end * h->C;
+	// d_io may hold the uploaded input; use the staging buffer for the output
+	rc = h->d_stage[0].ensure (bytes);
+	if (rc) return rc;
+	rc = launch_interleave (h, m_end, 0, (float*)h->d_stage[0].p, t_end);
+	if (rc) return rc;
+	CK (cudaMemcpyAsync (dst, h->d_stage[0].p, bytes, cudaMemcpyDeviceToHost, h->stream));
+	CK (cudaStreamSynchronize (h->stream));
+	h->stats.d2h_bytes += bytes;
+	return PHASEROT_OK;
+}
+
+int
+phaserot_render (phaserot_t* h, const float* interleaved, uint64_t n_frames, const int* angles, int flush_blocks, float* out)
+{
+	return render_bulk (h, interleaved, false, n_frames, angles, flush_blocks, out, false);
+}
+
+int
+phaserot_render_device (phaserot_t* h, const float* d_interleaved, uint64_t n_frames, const int* angles, int flush_blocks, float* d_out)
+{
+	return render_bulk (h, d_interleaved, true, n_frames, angles, flush_blocks, d_out, true);
+}
+
+uint32_t
+phaserot_latency (const phaserot_t* h)
+{
+	if (!h) {
+		return 0;
+	}
+	return h->plugin ? h->P + h->firlat : (uint32_t)h->L / 2;
+}
+
+int
+phaserot_process (phaserot_t* h, const float* const* in, float* const* out, uint32_t n_frames, const float* angle_deg)
+{
+	if (!h || !in || !out || !angle_deg) {
+		return PHASEROT_E_INVAL;
+	}
+	if (!h->plugin) {
+		return PHASEROT_E_STATE;
+	}
+	if (n_frames == 0) {
+		return PHASEROT_OK;
+	}
+	DevGuard       guard (h->dev);
+	const uint32_t P = h->P, firlen = h->firlen, keep = firlen + P, n = n_frames;
+	const int      C  = h->C;
+	const uint64_t t0 = h->ppos;
+
+	// Window per channel: W = [tail (keep) | new (n)]; output i in [0, n) is
+	// Y[u], u = t0 - P + i, at W index firlen + i.
+	const size_t wlen    = (size_t)keep + n;
+	const size_t wstride = (wlen + 3) & ~(size_t)3;
+	// Coefficient prefix per channel: what is left of the last completed
+	// partition, then every partition that completes in this call while the
+	// angle is still moving.  Everything after it uses the steady (ca, sa).
+	const uint32_t first_np = (uint32_t)(t0 / P);                  // partition being filled at t0
+	const uint32_t n_comp   = (uint32_t)((t0 + n) / P) - first_np; // partitions completing in this call
+	const size_t   pre_cap  = (size_t)P * 20;                      // a full 180 degree ramp is <= 9 partitions (src:295)
+	const bool     small    = n <= 16384;
+	const size_t   io_bytes = sizeof (float) * wstride * C + sizeof (float2) * pre_cap * C + (small ? sizeof (float) * (size_t)n * C : 0) + 64;
+	int            rc       = h->h_io.ensure (io_bytes);
+	if (rc) return rc;
+	float*  W    = (float*)h->h_io.p;
+	float2* pre  = (float2*)(W + wstride * C);
+	float*  yout = (float*)(pre + pre_cap * C);
+
+	float2 chan_cs[2];
+	int    ramp_len[2] = { 0, 0 };
+	for (int c = 0; c < C; ++c) {
+		float* w = W + wstride * c;
+		memcpy (w, h->ptail.data () + (size_t)c * keep, sizeof (float) * keep);
+		memcpy (w + keep, in[c], sizeof (float) * n);
+
+		PluginChan& ch = h->pch[(size_t)c];
+		float target   = angle_deg[c] / -360.f; // src:564-571
+		if (target < -.5f) target = -.5f;
+		if (target > 0.5f) target = 0.5f;
+
+		float2* pc       = pre + pre_cap * c;
+		size_t  plen     = 0; // prefix entries written
+		size_t  need_len = 0; // entries that differ from the steady coefficients
+		// outputs start at u = t0 - P: before the stream (zero) while t0 < P,
+		// otherwise inside the last completed partition
+		const uint32_t off0 = (uint32_t)(t0 % P);
+		if (t0 < P) {
+			for (uint32_t i = off0; i < P; ++i) pc[plen++] = make_float2 (0.f, 0.f);
+			need_len = plen;
+		} else {
+			for (uint32_t i = off0; i < P; ++i) pc[plen++] = ch.last_is_ramp ? ch.last[i] : ch.last_const;
+			if (ch.last_is_ramp) need_len = plen;
+		}
+		for (uint32_t k = 0; k < n_comp; ++k) {
+			if (target == ch.angle) {
+				// steady from here on: every remaining partition uses (ca, sa)
+				ch.last_is_ramp = false;
+				ch.last_const   = make_float2 (ch.ca, ch.sa);
+				break;
+			}
+			plugin_partition_coef (h, ch, target, ch.last.data ());
+			ch.last_is_ramp = true;
+			ch.last_const   = make_float2 (ch.ca, ch.sa);
+			if (plen + P > pre_cap) {
+				snprintf (g_last_error, sizeof (g_last_error), "angle ramp longer than %zu partitions", pre_cap / P);
+				return PHASEROT_E_UNSUPPORTED;
+			}
+			memcpy (pc + plen, ch.last.data (), sizeof (float2) * P);
+			plen += P;
+			need_len = plen;
+		}
+		ramp_len[c] = (int)std::min<size_t> (need_len, (size_t)n);
+		chan_cs[c]  = ch.last_const;
+		// new tail = last `keep` samples of W
+		memcpy (h->ptail.data () + (size_t)c * keep, w + wlen - keep, sizeof (float) * keep);
+	}
+	h->ppos += n;
+
+	if (small && h->h_io.d) {
+		// small call: direct-form FIR straight out of mapped pinned memory
+		const int    nodd = h->Lh;
+		const size_t smem = sizeof (float) * (3 * (size_t)nodd + 128);
+		static bool  attr = false;
+		if (!attr) {
+			CK (cudaFuncSetAttribute (fir_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+			attr = true;
+		}
+		const char*   dbase = (const char*)h->h_io.d;
+		const float*  dW    = (const float*)dbase;
+		const float2* dpre  = (const float2*)(dbase + ((const char*)pre - (const char*)h->h_io.p));
+		float*        dy    = (float*)(dbase + ((const char*)yout - (const char*)h->h_io.p));
+		FirCoef       fc;
+		for (int c = 0; c < 2; ++c) {
+			fc.cs[c]   = chan_cs[c < C ? c : 0];
+			fc.rlen[c] = ramp_len[c < C ? c : 0];
+		}
+		const dim3 grid ((n + 127) / 128, (unsigned)C);
+		fir_direct_kernel<<<grid, 128, smem, h->stream>>> (dW, (int)wstride, (int)wlen, (long long)wlen, (long long)firlen, (int)n,
+		                                                    (const float*)h->d_g.p, nodd, (int)h->firlat, dpre, (int)pre_cap, fc, dy, (int)n);
+		CK (cudaGetLastError ());
+		++h->stats.kernel_launches;
+		CK (cudaStreamSynchronize (h->stream));
+		for (int c = 0; c < C; ++c) {
+			memcpy (out[c], yout + (size_t)c * n, sizeof (float) * n);
+		}
+		h->stats.h2d_bytes += sizeof (float) * wlen * C;
+		h->stats.d2h_bytes += sizeof (float) * (size_t)n * C;
+		return PHASEROT_OK;
+	}
+
+	// bulk call: FFT convolution over W (planar already: one "channel-major" upload)
+	{
+		const long long t_end = (long long)wlen; // outputs wanted: W indices [firlen, wlen)
+		const long long m_end = (t_end + 1) / 2;
+		long long       nseg  = 0;
+		rc                    = ensure_planes (h, m_end, &nseg);
+		if (rc) return rc;
+		rc = init_front_pad (h, nullptr);
+		if (rc) return rc;
+		const long long n_fill = nseg * h->V;
+		for (int c = 0; c < C; ++c) {
+			float2* pl = (float2*)h->d_plane.p + (long long)c * h->plane_stride + h->padf;
+			CK (cudaMemcpyAsync (pl, W + wstride * c, sizeof (float) * wlen, cudaMemcpyHostToDevice, h->stream));
+			const long long have = (long long)(wlen / 2); // whole complex elements copied
+			if (wlen & 1) {
+				// odd tail sample: its partner must read as zero
+				CK (cudaMemsetAsync ((float*)(pl + have) + 1, 0, sizeof (float), h->stream));
+			}
+			const long long from = (long long)((wlen + 1) / 2);
+			if (n_fill > from) {
+				CK (cudaMemsetAsync (pl + from, 0, sizeof (float2) * (size_t)(n_fill - from), h->stream));
+			}
+		}
+		h->stats.h2d_bytes += sizeof (float) * wlen * C;
+		h->out_stride = (m_end + 3) & ~3LL;
+		rc            = h->d_out.ensure (sizeof (float2) * (size_t)h->out_stride * C);
+		if (rc) return rc;
+		rc = h->d_chancs.ensure (sizeof (float2) * (size_t)C);
+		if (rc) return rc;
+		// ramp table indexed by W sample index: prefix starts at W index firlen
+		size_t rmax = 0;
+		for (int c = 0; c < C; ++c) rmax = std::max (rmax, (size_t)ramp_len[c]);
+		const long long rstride = (long long)((firlen + rmax + 3) & ~(size_t)3);
+		std::vector<float2> ramp ((size_t)rstride * C, make_float2 (0.f, 0.f));
+		std::vector<int>    rl ((size_t)C);
+		for (int c = 0; c < C; ++c) {
+			memcpy (ramp.data () + (size_t)rstride * c + firlen, pre + pre_cap * c, sizeof (float2) * (size_t)ramp_len[c]);
+			rl[(size_t)c] = (int)firlen + ramp_len[c];
+		}
+		rc = h->d_ramp.ensure (sizeof (float2) * ramp.size ());
+		if (rc) return rc;
+		CK (cudaMemcpyAsync (h->d_ramp.p, ramp.data (), sizeof (float2) * ramp.size (), cudaMemcpyHostToDevice, h->stream));
+		CK (cudaMemcpyAsync (d_ramplen (h), rl.data (), sizeof (int) * (size_t)C, cudaMemcpyHostToDevice, h->stream));
+		CK (cudaMemcpyAsync (h->d_chancs.p, chan_cs, sizeof (float2) * (size_t)C, cudaMemcpyHostToDevice, h->stream));
+		CK (cudaStreamSynchronize (h->stream));
+
+		ConvParams p;
+		fill_conv_common (h, p);
+		p.chan0       = 0;
+		p.nchan       = C;
+		p.seg0        = 0;
+		p.nseg        = nseg;
+		p.m_end       = m_end;
+		p.out         = (float2*)h->d_out.p;
+		p.out_stride  = h->out_stride;
+		p.cs          = (const float2*)h->d_chancs.p;
+		p.ramp        = (const float2*)h->d_ramp.p;
+		p.ramp_stride = rstride;
+		p.ramp_len    = d_ramplen (h);
+		rc            = launch_conv<EPI_RENDER> (h, p);
+		if (rc) return rc;
+		// outputs live at W sample indices [firlen, firlen + n): plain float view of d_out
+		for (int c = 0; c < C; ++c) {
+			const float* src = (const float*)((float2*)h->d_out.p + (long long)c * h->out_stride) + firlen;
+			CK (cudaMemcpyAsync (out[c], src, sizeof (float) * n, cudaMemcpyDeviceToHost, h->stream));
+		}
+		CK (cudaStreamSynchronize (h->stream));
+		h->stats.d2h_bytes += sizeof (float) * (size_t)n * C;
+	}
+	return PHASEROT_OK;
+}
+
+int
+phaserot_get_stats (phaserot_t* h, phaserot_stats_t* out)
+{
+	if (!h || !out) {
+		return PHASEROT_E_INVAL;
+	}
+	*out = h->stats;
+	return PHASEROT_OK;
+}
+
+int
+phaserot_reset_stats (phaserot_t* h)
+{
+	if (!h) {
+		return PHASEROT_E_INVAL;
+	}
+	memset (&h->stats, 0, sizeof (h->stats));
+	return PHASEROT_OK;
+}
+
+} // extern "C"
