@@ -117,6 +117,24 @@ PHASEROT_API int phaserot_sweep (phaserot_t* h, const float* interleaved, uint64
 PHASEROT_API int phaserot_sweep_device (phaserot_t* h, const float* d_interleaved, uint64_t n_frames,
                                         int ang_start, int ang_end, int ang_stride, int chn);
 
+/* One shard of a longer stream, for sample-range sharding across GPUs: this
+ * handle examines output samples of frames [0, n_frames) of the shard, where
+ * the shard is preceded in the full stream by `hist` (blksiz frames,
+ * interleaved, HOST memory; NULL = silence / start of stream).
+ *   first != 0 : the shard starts the stream (first-block rule applies)
+ *   last  != 0 : the shard ends it (short block zero padded + zero flush block)
+ * Non-last shards must be a multiple of blksiz long.  Because a per-angle peak
+ * is a maximum over samples, the element-wise max of all shards' tables is the
+ * table of the whole stream (combine with an NCCL max all-reduce).  It equals
+ * the single-pass table bit for bit when every shard starts at a multiple of
+ * phaserot_shard_align() frames (the shards then cut the stream on the same
+ * FFT segment grid); otherwise it agrees to fp32 FFT rounding (~1e-6). */
+PHASEROT_API int phaserot_sweep_shard_device (phaserot_t* h, const float* d_interleaved, uint64_t n_frames,
+                                              const float* hist, int first, int last,
+                                              int ang_start, int ang_end, int ang_stride, int chn);
+
+PHASEROT_API uint32_t phaserot_shard_align (const phaserot_t* h);
+
 /* Block-streaming drop-in for PhaseRotate::analyze (cli:431-444): feed one
  * block of blksiz frames at a time (`start` != 0 for the first block of a
  * file, cli:571-582).  Blocks are staged and processed in large batches; the
@@ -149,6 +167,10 @@ PHASEROT_API int phaserot_apply (phaserot_t* h, float* buf, const int* angles);
 PHASEROT_API int phaserot_render (phaserot_t* h, const float* interleaved, uint64_t n_frames,
                                   const int* angles, int flush_blocks, float* out);
 
+/* After phaserot_render() the handle's apply() stream state is that of the
+ * last block processed (the zero flush block, or the last input block when
+ * flush_blocks == 0), so phaserot_apply() can continue the same stream. */
+
 /* Device-resident form: d_in / d_out are device pointers (same shapes). */
 PHASEROT_API int phaserot_render_device (phaserot_t* h, const float* d_interleaved, uint64_t n_frames,
                                          const int* angles, int flush_blocks, float* d_out);
@@ -169,6 +191,12 @@ PHASEROT_API uint32_t phaserot_latency (const phaserot_t* h);
 
 /* ---- misc -------------------------------------------------------------- */
 
+/* Page-locked host memory for audio buffers handed to sweep/render (makes the
+ * H2D/D2H copies asynchronous and full speed).  Optional: any host pointer is
+ * accepted by every call. */
+PHASEROT_API void* phaserot_alloc_host (uint64_t bytes);
+PHASEROT_API void  phaserot_free_host (void* p);
+
 /* Wait for all enqueued work of this handle and bring the peak table back. */
 PHASEROT_API int phaserot_sync (phaserot_t* h);
 
@@ -183,6 +211,18 @@ typedef struct phaserot_stats {
 } phaserot_stats_t;
 PHASEROT_API int phaserot_get_stats (phaserot_t* h, phaserot_stats_t* out);
 PHASEROT_API int phaserot_reset_stats (phaserot_t* h);
+
+/* Per-kernel device times, measured with CUDA events recorded on the handle's
+ * stream around every launch while profiling is on (bench.py's roofline leg).
+ * Index: 0 fftconv+filter (sweep), 1 angle sweep, 2 deinterleave/interleave,
+ * 3 fftconv+rotate (render), 4 direct FIR (plugin small calls), 5 other. */
+#define PHASEROT_NKERNELS 6
+typedef struct phaserot_ktimes {
+	double   ms[PHASEROT_NKERNELS];
+	uint64_t launches[PHASEROT_NKERNELS];
+} phaserot_ktimes_t;
+PHASEROT_API int phaserot_set_profiling (phaserot_t* h, int on);
+PHASEROT_API int phaserot_get_kernel_times (phaserot_t* h, phaserot_ktimes_t* out);
 
 PHASEROT_API const char* phaserot_strerror (int code);
 /* Text of the last CUDA failure on this thread ("" if none). */

@@ -23,7 +23,9 @@ SYMBOLS = [
     "phaserot_sweep", "phaserot_sweep_device", "phaserot_analyze", "phaserot_peak", "phaserot_peaks", "phaserot_lut",
     "phaserot_apply", "phaserot_render", "phaserot_render_device",
     "phaserot_process", "phaserot_latency",
+    "phaserot_sweep_shard_device", "phaserot_shard_align", "phaserot_set_profiling", "phaserot_get_kernel_times",
     "phaserot_sync", "phaserot_get_stats", "phaserot_reset_stats",
+    "phaserot_alloc_host", "phaserot_free_host",
     "phaserot_strerror", "phaserot_last_error", "phaserot_abi_version",
 ]
 
@@ -38,6 +40,14 @@ class Cfg(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("points_total", C.c_uint64), ("points_evaluated", C.c_uint64),
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+
+
+NKERNELS = 6
+KERNEL_NAMES = ["fftconv_filter", "sweep", "deinterleave", "fftconv_render", "fir_direct", "other"]
+
+
+class KTimes(C.Structure):
+    _fields_ = [("ms", C.c_double * NKERNELS), ("launches", C.c_uint64 * NKERNELS)]
 
 
 class PhaserotError(RuntimeError):
@@ -81,9 +91,18 @@ def load():
     lib.phaserot_process.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.c_uint32, vp]
     lib.phaserot_latency.argtypes = [vp]
     lib.phaserot_latency.restype = C.c_uint32
+    lib.phaserot_sweep_shard_device.argtypes = [vp, vp, C.c_uint64, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.phaserot_shard_align.argtypes = [vp]
+    lib.phaserot_shard_align.restype = C.c_uint32
+    lib.phaserot_set_profiling.argtypes = [vp, C.c_int]
+    lib.phaserot_get_kernel_times.argtypes = [vp, C.POINTER(KTimes)]
     lib.phaserot_sync.argtypes = [vp]
     lib.phaserot_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.phaserot_reset_stats.argtypes = [vp]
+    lib.phaserot_alloc_host.argtypes = [C.c_uint64]
+    lib.phaserot_alloc_host.restype = C.c_void_p
+    lib.phaserot_free_host.argtypes = [vp]
+    lib.phaserot_free_host.restype = None
     lib.phaserot_strerror.argtypes = [C.c_int]
     lib.phaserot_strerror.restype = C.c_char_p
     lib.phaserot_last_error.restype = C.c_char_p
@@ -156,6 +175,29 @@ class Phaserot:
         if ang_end is None:
             ang_end = self.maxsample
         self._ck(self._lib.phaserot_sweep_device(self._h, C.c_void_p(dev_ptr), n_frames, ang_start, ang_end, stride, chn), "phaserot_sweep_device")
+
+    def sweep_shard_device(self, dev_ptr, n_frames, hist, first, last, ang_start=0, ang_end=None, stride=1, chn=-1):
+        """hist: host array [blksiz, channels] float32 or None."""
+        if ang_end is None:
+            ang_end = self.maxsample
+        hp = None
+        if hist is not None:
+            hist = np.ascontiguousarray(hist, np.float32)
+            assert hist.size == self.blksiz * self.n_channels
+            hp = _ptr(hist)
+        self._ck(self._lib.phaserot_sweep_shard_device(self._h, C.c_void_p(dev_ptr), n_frames, hp, int(first), int(last),
+                                                       ang_start, ang_end, stride, chn), "phaserot_sweep_shard_device")
+
+    def shard_align(self):
+        return int(self._lib.phaserot_shard_align(self._h))
+
+    def set_profiling(self, on):
+        self._ck(self._lib.phaserot_set_profiling(self._h, int(on)), "phaserot_set_profiling")
+
+    def kernel_times(self):
+        k = KTimes()
+        self._ck(self._lib.phaserot_get_kernel_times(self._h, C.byref(k)), "phaserot_get_kernel_times")
+        return {KERNEL_NAMES[i]: {"ms": float(k.ms[i]), "launches": int(k.launches[i])} for i in range(NKERNELS)}
 
     def analyze(self, block, ang_start=0, ang_end=180, stride=1, chn=-1, start=False):
         block = np.ascontiguousarray(block, np.float32)

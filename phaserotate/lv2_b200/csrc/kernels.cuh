@@ -36,10 +36,16 @@ constexpr int kSmemBytes   = kSmemElems * (int)sizeof (float2);
 
 enum { EPI_POINTS = 0, EPI_RENDER = 1, EPI_HILBERT = 2 };
 
+enum { SRC_PLANE = 0, SRC_INTER = 1 };
+
 struct ConvParams {
-	const float2* plane;        // [n_chan][plane_stride], element (padf + n) = z[n]
+	const float2* plane;        // SRC_PLANE: [n_chan][plane_stride], element (padf + n) = z[n]
 	long long     plane_stride;
 	int           padf;
+	const float*  inter;        // SRC_INTER: interleaved frames [n_frames][C], frame 0 = stream position 0
+	const float*  hist;         // SRC_INTER: interleaved frames [-2 Lh, 0) preceding the stream, or nullptr (silence)
+	long long     n_frames;     // SRC_INTER: frames present in `inter`
+	int           C;            // SRC_INTER: channels per frame
 	const float2* G;            // [kM] filter spectrum / kM, in the forward pass's output order
 	const float2* tw1;          // [6][1024]  W_M^(j q),    q in {1,2,3,4,8,12}
 	const float2* tw2;          // [6][64]    W_1024^(j q)
@@ -48,6 +54,7 @@ struct ConvParams {
 	int           V;            // valid complex outputs per segment = kM - Lh
 	int           chan0;        // first channel of this launch
 	long long     seg0;         // first segment
+	long long     seg_stride;   // segment index step (1 = contiguous; > 1 = sparse bootstrap sample)
 	long long     nseg;         // segments per channel in this launch
 	int           nchan;
 	long long     m_end;        // outputs exist for complex index m < m_end
@@ -59,7 +66,6 @@ struct ConvParams {
 	unsigned*     count;        // [n_chan]
 	const float*  thr2;         // [n_chan] squared filter radius
 	unsigned*     rawpeak;      // [n_chan] bits of max |x|
-	unsigned long long* n_seen; // points examined (stats)
 	// EPI_RENDER / EPI_HILBERT
 	float2*       out;          // [n_chan][out_stride], element m
 	long long     out_stride;
@@ -175,28 +181,80 @@ __device__ __forceinline__ float2 apply_tw (float2 v, const Tw6& t, int q)
 	return v;
 }
 
+// Segment input loaders: z[n0 + idx] for the first forward pass and the direct
+// branch of the epilogue.
+struct PlaneLoader { // planar float2 stream
+	const float2* src;
+	__device__ __forceinline__ float2 operator() (int idx) const { return __ldg (src + idx); }
+};
+struct Inter1Loader { // mono: the interleaved stream is the plane
+	const float2* src;
+	__device__ __forceinline__ float2 operator() (int idx) const { return __ldg (src + idx); }
+};
+struct Inter2Loader { // stereo: one 16 byte load = frames 2n, 2n+1 of both channels
+	const float4* src;
+	int           chan;
+	__device__ __forceinline__ float2 operator() (int idx) const
+	{
+		const float4 v = __ldg (src + idx);
+		return chan ? make_float2 (v.y, v.w) : make_float2 (v.x, v.z);
+	}
+};
+struct InterNLoader { // any channel count, two scalar loads
+	const float* src; // &inter[(2 n0) * C + c]
+	int          C;
+	__device__ __forceinline__ float2 operator() (int idx) const
+	{
+		const float* a = src + (long long)(2 * idx) * C;
+		return make_float2 (__ldg (a), __ldg (a + C));
+	}
+};
+struct EdgeLoader { // segments that touch the stream start (history / silence) or its end (zero padding)
+	const float* inter;
+	const float* hist;
+	long long    n_frames, f0; // f0 = frame index of idx 0 (= 2 n0)
+	int          C, c, L;      // L = frames of history available
+	__device__ __forceinline__ float at (long long f) const
+	{
+		if (f >= 0) return f < n_frames ? __ldg (inter + f * C + c) : 0.f;
+		return (hist && f >= -(long long)L) ? __ldg (hist + (L + f) * C + c) : 0.f;
+	}
+	__device__ __forceinline__ float2 operator() (int idx) const
+	{
+		const long long f = f0 + 2 * (long long)idx;
+		return make_float2 (at (f), at (f + 1));
+	}
+};
+
 // One radix-16 pass over the whole segment held in shared memory.
 // Butterfly e: block = e / STRIDE (size 16 * STRIDE), j = e % STRIDE.
 // Forward (DIF): u = data[j + k STRIDE]; y = DFT16(u); store y[q] * W^(j q) at q.
 // Inverse (DIT): y[q] * conj W^(j q); u = IDFT16; store u[k] at k.
-template <int DIR, int STRIDE, bool FROM_GLOBAL>
-__device__ __forceinline__ void pass16 (float2* sm, const float2* __restrict__ tw, const float2* __restrict__ gsrc, int tid)
+struct NoLoader {
+	__device__ __forceinline__ float2 operator() (int) const { return make_float2 (0.f, 0.f); }
+};
+
+template <int DIR, int STRIDE, bool FROM_GLOBAL, class Loader = NoLoader>
+__device__ __forceinline__ void pass16 (float2* sm, const float2* __restrict__ tw, int tid, const Loader ld = Loader ())
 {
+	// padded distance between two inputs of one butterfly (see phys())
+	constexpr int PS = STRIDE >= 64 ? STRIDE + STRIDE / 16 : STRIDE;
 #pragma unroll 1
 	for (int e = tid; e < kM / 16; e += kConvThreads) {
 		const int blk  = e / STRIDE;
 		const int j    = e - blk * STRIDE;
 		const int base = blk * (16 * STRIDE) + j;
+		float2*   sp   = sm + phys (base);
 		float2    u[16];
 		if (FROM_GLOBAL) {
 #pragma unroll
 			for (int k = 0; k < 16; ++k) {
-				u[k] = __ldcs (gsrc + base + k * STRIDE);
+				u[k] = ld (base + k * STRIDE);
 			}
 		} else {
 #pragma unroll
 			for (int k = 0; k < 16; ++k) {
-				u[k] = sm[phys (base + k * STRIDE)];
+				u[k] = sp[k * PS];
 			}
 		}
 		const Tw6 t = load_tw (tw, STRIDE, j);
@@ -213,7 +271,7 @@ __device__ __forceinline__ void pass16 (float2* sm, const float2* __restrict__ t
 			if (DIR < 0 && q) {
 				v = apply_tw<false> (v, t, q);
 			}
-			sm[phys (base + q * STRIDE)] = v;
+			sp[q * PS] = v;
 		}
 	}
 }
@@ -222,14 +280,21 @@ __device__ __forceinline__ void pass16 (float2* sm, const float2* __restrict__ t
 // on the same four shared-memory elements.
 __device__ __forceinline__ void mid_pass (float2* sm, const float2* __restrict__ G, int tid)
 {
-#pragma unroll 2
-	for (int e = tid; e < kM / 4; e += kConvThreads) {
-		float4*      p  = reinterpret_cast<float4*> (sm + phys (4 * e));
-		float4       v0 = p[0], v1 = p[1];
-		const float4 g0 = __ldg (reinterpret_cast<const float4*> (G + 4 * e));
-		const float4 g1 = __ldg (reinterpret_cast<const float4*> (G + 4 * e) + 1);
-		float2       a0 = make_float2 (v0.x, v0.y), a1 = make_float2 (v0.z, v0.w);
-		float2       a2 = make_float2 (v1.x, v1.y), a3 = make_float2 (v1.z, v1.w);
+	const float4* G4 = reinterpret_cast<const float4*> (G);
+	constexpr int kIter = kM / 4 / kConvThreads;
+	float4 g0 = __ldg (G4 + 2 * tid), g1 = __ldg (G4 + 2 * tid + 1);
+#pragma unroll
+	for (int it = 0; it < kIter; ++it) {
+		const int e  = tid + it * kConvThreads;
+		float4    n0 = g0, n1 = g1;
+		if (it + 1 < kIter) { // next iteration's spectrum values are in flight while this one computes
+			n0 = __ldg (G4 + 2 * (e + kConvThreads));
+			n1 = __ldg (G4 + 2 * (e + kConvThreads) + 1);
+		}
+		float4* p  = reinterpret_cast<float4*> (sm + phys (4 * e));
+		float4  v0 = p[0], v1 = p[1];
+		float2  a0 = make_float2 (v0.x, v0.y), a1 = make_float2 (v0.z, v0.w);
+		float2  a2 = make_float2 (v1.x, v1.y), a3 = make_float2 (v1.z, v1.w);
 		dft4<-1> (a0, a1, a2, a3);
 		a0 = cmul (a0, make_float2 (g0.x, g0.y));
 		a1 = cmul (a1, make_float2 (g0.z, g0.w));
@@ -238,6 +303,8 @@ __device__ __forceinline__ void mid_pass (float2* sm, const float2* __restrict__
 		dft4<+1> (a0, a1, a2, a3);
 		p[0] = make_float4 (a0.x, a0.y, a1.x, a1.y);
 		p[1] = make_float4 (a2.x, a2.y, a3.x, a3.y);
+		g0   = n0;
+		g1   = n1;
 	}
 }
 
@@ -252,125 +319,223 @@ __device__ __forceinline__ unsigned lanemask_lt ()
 // K1: FFT convolution with fused epilogue.  Persistent: one CTA per SM walks
 // (channel, segment) pairs.
 // ---------------------------------------------------------------------------
-template <int EPI>
-__global__ void __launch_bounds__ (kConvThreads, 1) fftconv_kernel (const ConvParams p)
+// warp-aggregated append of up to two points per lane to the survivor list
+__device__ __forceinline__ void append_points (float2* lst, unsigned* cnt, bool k0, float2 p0, bool k1, float2 p1, unsigned lt, int lane)
 {
-	extern __shared__ __align__ (16) float2 sm[];
-	const int tid = threadIdx.x;
+	const unsigned b0 = __ballot_sync (0xffffffffu, k0);
+	const unsigned b1 = __ballot_sync (0xffffffffu, k1);
+	if (b0 | b1) {
+		const int n0   = __popc (b0);
+		unsigned  base = 0;
+		if (lane == 0) base = atomicAdd (cnt, (unsigned)(n0 + __popc (b1)));
+		base = __shfl_sync (0xffffffffu, base, 0);
+		if (k0) lst[base + __popc (b0 & lt)] = p0;
+		if (k1) lst[base + n0 + __popc (b1 & lt)] = p1;
+	}
+}
 
-	float     rawmax    = 0.f;
-	int       raw_chan  = -1;
-	unsigned  seen      = 0;
+// Forward passes, spectrum multiply and inverse passes of one segment; the
+// first pass pulls its input through `ld`.
+template <class Loader>
+__device__ __forceinline__ void transform_segment (float2* sm, const ConvParams& p, int tid, const Loader ld)
+{
+	pass16<-1, 1024, true> (sm, p.tw1, tid, ld);
+	__syncthreads ();
+	pass16<-1, 64, false> (sm, p.tw2, tid);
+	__syncthreads ();
+	pass16<-1, 4, false> (sm, p.tw3, tid);
+	__syncthreads ();
+	mid_pass (sm, p.G, tid);
+	__syncthreads ();
+	pass16<+1, 4, false> (sm, p.tw3, tid);
+	__syncthreads ();
+	pass16<+1, 64, false> (sm, p.tw2, tid);
+	__syncthreads ();
+	pass16<+1, 1024, false> (sm, p.tw1, tid);
+	__syncthreads ();
+}
 
-	const long long total = p.nseg * p.nchan;
-	for (long long w = blockIdx.x; w < total; w += gridDim.x) {
-		const int       ci  = (int)(w / p.nseg);
-		const long long seg = p.seg0 + (w - (long long)ci * p.nseg);
-		const int       c   = p.chan0 + ci;
-		// segment input: z[seg V - Lh .. seg V - Lh + M)
-		const float2* zc  = p.plane + (long long)c * p.plane_stride + p.padf;
-		const float2* src = zc + seg * p.V - p.Lh;
+// Epilogue state shared by the loader-specific instantiations.
+struct EpiCtx {
+	int       c, i_hi, i_skip, i_zero;
+	long long mbase;
+	float     rawmax;
+};
 
-		if (EPI == EPI_POINTS && c != raw_chan) {
-			if (raw_chan >= 0) {
-				// flush running raw peak of the previous channel
-				for (int o = 16; o; o >>= 1) rawmax = fmaxf (rawmax, __shfl_xor_sync (0xffffffffu, rawmax, o));
-				if ((tid & 31) == 0) atomicMax (p.rawpeak + raw_chan, __float_as_uint (rawmax));
-			}
-			raw_chan = c;
-			rawmax   = 0.f;
-		}
-
-		pass16<-1, 1024, true> (sm, p.tw1, src, tid);
-		__syncthreads ();
-		pass16<-1, 64, false> (sm, p.tw2, nullptr, tid);
-		__syncthreads ();
-		pass16<-1, 4, false> (sm, p.tw3, nullptr, tid);
-		__syncthreads ();
-		mid_pass (sm, p.G, tid);
-		__syncthreads ();
-		pass16<+1, 4, false> (sm, p.tw3, nullptr, tid);
-		__syncthreads ();
-		pass16<+1, 64, false> (sm, p.tw2, nullptr, tid);
-		__syncthreads ();
-		pass16<+1, 1024, false> (sm, p.tw1, nullptr, tid);
-		__syncthreads ();
-
-		// epilogue over the V valid outputs: local index i in [Lh, M), m = seg V + (i - Lh)
-		const long long mbase = seg * p.V - p.Lh; // m = mbase + i
-		if (EPI == EPI_POINTS) {
-			const float thr2 = p.thr2[c];
-			float2*     lst  = p.list + (long long)c * p.list_stride;
-			unsigned*   cnt  = p.count + c;
-			const unsigned lt = lanemask_lt ();
-			for (int i0 = p.Lh; i0 < kM; i0 += kConvThreads) {
-				const int       i  = i0 + tid;
-				const long long m  = mbase + i;
-				bool            k0 = false, k1 = false;
-				float2          p0 = make_float2 (0.f, 0.f), p1 = p0;
-				if (m < p.m_end) {
-					const float2 c1 = sm[phys (i)];
-					const float2 c0 = sm[phys (i - 1)];
-					float2       zd = __ldg (zc + (m - (p.Lh >> 1)));
-					rawmax          = fmaxf (rawmax, fmaxf (fabsf (zd.x), fabsf (zd.y)));
-					if (m >= p.m_skip) {
-						if (m < p.m_zero) zd = make_float2 (0.f, 0.f);
-						p0 = make_float2 (zd.x, c0.y); // t = 2m   : (x_d, H)
-						p1 = make_float2 (zd.y, c1.x); // t = 2m+1
-						k0 = fmaf (p0.x, p0.x, p0.y * p0.y) >= thr2;
-						k1 = fmaf (p1.x, p1.x, p1.y * p1.y) >= thr2;
-						seen += 2;
-					}
-				}
-				const unsigned b0 = __ballot_sync (0xffffffffu, k0);
-				const unsigned b1 = __ballot_sync (0xffffffffu, k1);
-				if (b0 | b1) {
-					const int n0 = __popc (b0), n1 = __popc (b1);
-					unsigned  base = 0;
-					if ((tid & 31) == 0) base = atomicAdd (cnt, (unsigned)(n0 + n1));
-					base = __shfl_sync (0xffffffffu, base, 0);
-					if (k0) lst[base + __popc (b0 & lt)] = p0;
-					if (k1) lst[base + n0 + __popc (b1 & lt)] = p1;
+// Epilogue over the valid outputs: local index i in [Lh, M), complex index m = mbase + i.
+//   H[2m] = Im w[m-1], H[2m+1] = Re w[m];  direct branch x_d pair = z[m - Lh/2] = ld (i - Lh/2).
+template <int EPI, class Loader>
+__device__ __forceinline__ void epilogue (float2* sm, const ConvParams& p, int tid, int lane, EpiCtx& cx, const Loader ld)
+{
+	const int dl = p.Lh >> 1;
+	if (EPI == EPI_POINTS) {
+		const float    thr2 = p.thr2[cx.c];
+		float2*        lst  = p.list + (long long)cx.c * p.list_stride;
+		unsigned*      cnt  = p.count + cx.c;
+		const unsigned lt   = lanemask_lt ();
+		float          rawmax = cx.rawmax;
+		const bool interior = (cx.i_hi == kM) && (cx.i_skip == p.Lh) && (cx.i_zero == p.Lh);
+		if (interior) {
+			// two complex outputs (four samples) per thread and iteration, no bounds logic
+			for (int i = p.Lh + 2 * tid; i < kM; i += 2 * kConvThreads) {
+				const float4 cc = *reinterpret_cast<const float4*> (sm + phys (i)); // w[i], w[i+1]
+				const float2 cm = sm[phys (i - 1)];
+				const float2 za = ld (i - dl), zb = ld (i + 1 - dl);
+				rawmax = fmaxf (fmaxf (rawmax, fmaxf (fabsf (za.x), fabsf (za.y))), fmaxf (fabsf (zb.x), fabsf (zb.y)));
+				const float r0 = fmaf (za.x, za.x, cm.y * cm.y);
+				const float r1 = fmaf (za.y, za.y, cc.x * cc.x);
+				const float r2 = fmaf (zb.x, zb.x, cc.y * cc.y);
+				const float r3 = fmaf (zb.y, zb.y, cc.z * cc.z);
+				const bool  any = !(fmaxf (fmaxf (r0, r1), fmaxf (r2, r3)) < thr2);
+				if (__any_sync (0xffffffffu, any)) {
+					append_points (lst, cnt, r0 >= thr2, make_float2 (za.x, cm.y), r1 >= thr2, make_float2 (za.y, cc.x), lt, lane);
+					append_points (lst, cnt, r2 >= thr2, make_float2 (zb.x, cc.y), r3 >= thr2, make_float2 (zb.y, cc.z), lt, lane);
 				}
 			}
 		} else {
-			float2*      outc = p.out + (long long)c * p.out_stride;
-			const float2 cs   = (EPI == EPI_RENDER) ? p.cs[c] : make_float2 (0.f, 1.f);
-			const int    rlen = (EPI == EPI_RENDER && p.ramp_len) ? p.ramp_len[c] : 0;
-			for (int i = p.Lh + tid; i < kM; i += kConvThreads) {
-				const long long m = mbase + i;
-				if (m < p.m_end) {
+			// edge segment (stream start / end): per element region checks
+			for (int i0 = p.Lh; i0 < kM; i0 += kConvThreads) {
+				const int i  = i0 + tid;
+				bool      k0 = false, k1 = false;
+				float2    p0 = make_float2 (0.f, 0.f), p1 = p0;
+				if (i < cx.i_hi) {
 					const float2 c1 = sm[phys (i)];
 					const float2 c0 = sm[phys (i - 1)];
-					float2       y  = make_float2 (c0.y, c1.x);
-					if (EPI == EPI_RENDER) {
-						const float2 zd  = __ldg (zc + (m - (p.Lh >> 1)));
-						float2       cs0 = cs, cs1 = cs;
-						if (2 * m < rlen) {
-							const float2* r = p.ramp + (long long)c * p.ramp_stride + 2 * m;
-							cs0             = r[0];
-							if (2 * m + 1 < rlen) cs1 = r[1];
-						}
-						// mul, mul, add like the reference (cli:223, src:700,715)
-						y.x = __fadd_rn (__fmul_rn (cs0.x, zd.x), __fmul_rn (cs0.y, c0.y));
-						y.y = __fadd_rn (__fmul_rn (cs1.x, zd.y), __fmul_rn (cs1.y, c1.x));
+					float2       zd = ld (i - dl);
+					rawmax          = fmaxf (rawmax, fmaxf (fabsf (zd.x), fabsf (zd.y)));
+					if (i >= cx.i_skip) {
+						if (i < cx.i_zero) zd = make_float2 (0.f, 0.f);
+						p0 = make_float2 (zd.x, c0.y);
+						p1 = make_float2 (zd.y, c1.x);
+						k0 = fmaf (p0.x, p0.x, p0.y * p0.y) >= thr2;
+						k1 = fmaf (p1.x, p1.x, p1.y * p1.y) >= thr2;
 					}
-					__stcs (outc + m, y);
 				}
+				append_points (lst, cnt, k0, p0, k1, p1, lt, lane);
+			}
+		}
+		cx.rawmax = rawmax;
+	} else {
+		float2*      outc = p.out + (cx.mbase + (long long)cx.c * p.out_stride);
+		const float2 cs   = (EPI == EPI_RENDER) ? p.cs[cx.c] : make_float2 (0.f, 1.f);
+		const int    rlen = (EPI == EPI_RENDER && p.ramp_len) ? p.ramp_len[cx.c] : 0;
+		for (int i = p.Lh + tid; i < cx.i_hi; i += kConvThreads) {
+			const float2 c1 = sm[phys (i)];
+			const float2 c0 = sm[phys (i - 1)];
+			float2       y  = make_float2 (c0.y, c1.x);
+			if (EPI == EPI_RENDER) {
+				const float2    zd  = ld (i - dl);
+				float2          cs0 = cs, cs1 = cs;
+				const long long t0  = 2 * (cx.mbase + i);
+				if (t0 < rlen) {
+					const float2* r = p.ramp + (long long)cx.c * p.ramp_stride + t0;
+					cs0             = r[0];
+					if (t0 + 1 < rlen) cs1 = r[1];
+				}
+				// mul, mul, add like the reference (cli:223, src:700,715)
+				y.x = __fadd_rn (__fmul_rn (cs0.x, zd.x), __fmul_rn (cs0.y, c0.y));
+				y.y = __fadd_rn (__fmul_rn (cs1.x, zd.y), __fmul_rn (cs1.y, c1.x));
+			}
+			__stcs (outc + i, y);
+		}
+	}
+}
+
+template <int EPI, class Loader>
+__device__ __forceinline__ void run_segment (float2* sm, const ConvParams& p, int tid, int lane, EpiCtx& cx, const Loader ld)
+{
+	transform_segment (sm, p, tid, ld);
+	epilogue<EPI> (sm, p, tid, lane, cx, ld);
+}
+
+// ---------------------------------------------------------------------------
+// K1: FFT convolution with fused epilogue.  Persistent: one CTA per SM walks
+// (segment, channel) pairs, channel fastest, so that the CTAs working on the
+// channels of one stretch of interleaved input run at the same time and share
+// it through L2.
+// ---------------------------------------------------------------------------
+template <int EPI, int SRC>
+__global__ void __launch_bounds__ (kConvThreads, 1) fftconv_kernel (const ConvParams p)
+{
+	extern __shared__ __align__ (16) float2 sm[];
+	const int tid  = threadIdx.x;
+	const int lane = tid & 31;
+
+	EpiCtx cx;
+	cx.rawmax    = 0.f;
+	int raw_chan = -1;
+
+	const long long total = p.nseg * p.nchan;
+	for (long long w = blockIdx.x; w < total; w += gridDim.x) {
+		const long long si  = w / p.nchan;
+		const int       ci  = (int)(w - si * p.nchan);
+		const long long seg = p.seg0 + si * p.seg_stride;
+		const int       c   = p.chan0 + ci;
+		const long long n0  = seg * p.V - p.Lh; // complex stream index of local index 0
+
+		if (EPI == EPI_POINTS && c != raw_chan) {
+			if (raw_chan >= 0) {
+				// flush the running raw peak of the previous channel
+				float r = cx.rawmax;
+				for (int o = 16; o; o >>= 1) r = fmaxf (r, __shfl_xor_sync (0xffffffffu, r, o));
+				if (lane == 0) atomicMax (p.rawpeak + raw_chan, __float_as_uint (r));
+			}
+			raw_chan  = c;
+			cx.rawmax = 0.f;
+		}
+		{
+			// pull this CTA's next segment towards L2 while this one is transformed
+			const long long wn = w + gridDim.x;
+			if (wn < total) {
+				const long long sn  = wn / p.nchan;
+				const int       cn  = (int)(wn - sn * p.nchan);
+				const long long nn0 = (p.seg0 + sn * p.seg_stride) * p.V - p.Lh;
+				const char*     pf;
+				long long       nbytes;
+				if (SRC == SRC_PLANE) {
+					pf     = reinterpret_cast<const char*> (p.plane + (long long)(p.chan0 + cn) * p.plane_stride + p.padf + nn0);
+					nbytes = (long long)kM * (long long)sizeof (float2);
+				} else {
+					pf     = reinterpret_cast<const char*> (p.inter + 2 * nn0 * p.C);
+					nbytes = (cn == 0 && nn0 >= 0 && 2 * (nn0 + kM) <= p.n_frames) ? (long long)kM * 2 * p.C * (long long)sizeof (float) : 0;
+				}
+				for (long long l = (long long)tid * 128; l < nbytes; l += (long long)kConvThreads * 128) {
+					asm volatile ("prefetch.global.L2 [%0];" ::"l"(pf + l));
+				}
+			}
+		}
+
+		// local bounds of the output regions (clamped to the segment)
+		cx.c     = c;
+		cx.mbase = n0;
+		{
+			const long long hi = p.m_end - n0, sk = p.m_skip - n0, ze = p.m_zero - n0;
+			cx.i_hi   = hi >= kM ? kM : (hi <= p.Lh ? p.Lh : (int)hi);
+			cx.i_skip = sk <= p.Lh ? p.Lh : (sk >= kM ? kM : (int)sk);
+			cx.i_zero = ze <= p.Lh ? p.Lh : (ze >= kM ? kM : (int)ze);
+		}
+
+		if (SRC == SRC_PLANE) {
+			run_segment<EPI> (sm, p, tid, lane, cx, PlaneLoader { p.plane + (long long)c * p.plane_stride + p.padf + n0 });
+		} else {
+			const bool inside = n0 >= 0 && 2 * (n0 + kM) <= p.n_frames;
+			if (!inside) {
+				run_segment<EPI> (sm, p, tid, lane, cx, EdgeLoader { p.inter, p.hist, p.n_frames, 2 * n0, p.C, c, 2 * p.Lh });
+			} else if (p.C == 2 && (reinterpret_cast<uintptr_t> (p.inter) & 15) == 0) {
+				run_segment<EPI> (sm, p, tid, lane, cx, Inter2Loader { reinterpret_cast<const float4*> (p.inter) + n0, c });
+			} else if (p.C == 1 && (reinterpret_cast<uintptr_t> (p.inter) & 7) == 0) {
+				run_segment<EPI> (sm, p, tid, lane, cx, Inter1Loader { reinterpret_cast<const float2*> (p.inter) + n0 });
+			} else {
+				run_segment<EPI> (sm, p, tid, lane, cx, InterNLoader { p.inter + 2 * n0 * p.C + c, p.C });
 			}
 		}
 		__syncthreads (); // smem is overwritten by the next segment's first pass
 	}
 
-	if (EPI == EPI_POINTS) {
-		if (raw_chan >= 0) {
-			for (int o = 16; o; o >>= 1) rawmax = fmaxf (rawmax, __shfl_xor_sync (0xffffffffu, rawmax, o));
-			if ((tid & 31) == 0) atomicMax (p.rawpeak + raw_chan, __float_as_uint (rawmax));
-		}
-		if (p.n_seen) {
-			for (int o = 16; o; o >>= 1) seen += __shfl_xor_sync (0xffffffffu, seen, o);
-			if ((tid & 31) == 0 && seen) atomicAdd (p.n_seen, (unsigned long long)seen);
-		}
+	if (EPI == EPI_POINTS && raw_chan >= 0) {
+		float r = cx.rawmax;
+		for (int o = 16; o; o >>= 1) r = fmaxf (r, __shfl_xor_sync (0xffffffffu, r, o));
+		if (lane == 0) atomicMax (p.rawpeak + raw_chan, __float_as_uint (r));
 	}
 }
 

@@ -226,7 +226,7 @@ struct phaserot {
 	std::vector<float> table; // [C][MS]  == PhaseRotate::_peak
 
 	DevBuf d_G, d_tw, d_g;
-	DevBuf d_plane, d_out, d_list, d_stage[2], d_io;
+	DevBuf d_plane, d_out, d_list, d_stage[2], d_io, d_inter, d_hist;
 	DevBuf d_small; // count[C] | thr2[C] | raw[C] | ramp_len[C] | stats[2 x u64]
 	DevBuf d_cs, d_peaks, d_ramp, d_chancs;
 	PinBuf h_stage[2], h_res, h_io;
@@ -255,6 +255,13 @@ struct phaserot {
 	uint64_t                ppos = 0;
 
 	phaserot_stats_t stats {};
+
+	// profiling: event pairs around launches, resolved at the next sync
+	bool                     prof = false;
+	std::vector<cudaEvent_t> prof_ev;   // pool, pairs
+	std::vector<int>         prof_kind; // kind per used pair
+	size_t                   prof_used = 0;
+	phaserot_ktimes_t        ktimes {};
 };
 
 namespace {
@@ -280,6 +287,46 @@ struct DevGuard {
 
 // d_small: count[64] | thr2[64] | raw[64] | ramp_len[64] | stats[2 x u64]
 constexpr size_t kSmallBytes = 4 * 64 * sizeof (int) + 2 * sizeof (unsigned long long);
+struct ProfScope {
+	phaserot* h;
+	size_t    slot = (size_t)-1;
+	ProfScope (phaserot* h_, int kind) : h (h_)
+	{
+		if (!h->prof) return;
+		if ((h->prof_used + 1) * 2 > h->prof_ev.size ()) {
+			for (int i = 0; i < 2; ++i) {
+				cudaEvent_t e;
+				if (cudaEventCreate (&e) != cudaSuccess) return;
+				h->prof_ev.push_back (e);
+			}
+		}
+		slot = h->prof_used++;
+		h->prof_kind.resize (h->prof_used);
+		h->prof_kind[slot] = kind;
+		cudaEventRecord (h->prof_ev[2 * slot], h->stream);
+	}
+	~ProfScope ()
+	{
+		if (slot != (size_t)-1) cudaEventRecord (h->prof_ev[2 * slot + 1], h->stream);
+	}
+};
+
+// call after the stream is synchronised
+void
+prof_resolve (phaserot* h)
+{
+	for (size_t i = 0; i < h->prof_used; ++i) {
+		float ms = 0.f;
+		if (cudaEventElapsedTime (&ms, h->prof_ev[2 * i], h->prof_ev[2 * i + 1]) == cudaSuccess) {
+			h->ktimes.ms[h->prof_kind[i]] += ms;
+			h->ktimes.launches[h->prof_kind[i]] += 1;
+		} else {
+			cudaGetLastError ();
+		}
+	}
+	h->prof_used = 0;
+}
+
 unsigned*           d_count (phaserot* h) { return (unsigned*)h->d_small.p; }
 float*              d_thr2 (phaserot* h) { return (float*)h->d_small.p + 64; }
 unsigned*           d_raw (phaserot* h) { return (unsigned*)h->d_small.p + 128; }
@@ -346,23 +393,25 @@ fill_conv_common (phaserot* h, ConvParams& p)
 	p.tw3          = p.tw2 + 6 * 64;
 	p.Lh           = h->Lh;
 	p.V            = h->V;
+	p.seg_stride   = 1;
 }
 
-template <int EPI>
+template <int EPI, int SRC = SRC_PLANE>
 int
 launch_conv (phaserot* h, const ConvParams& p)
 {
-	static bool attr_done[3] = { false, false, false };
-	if (!attr_done[EPI]) {
-		CK (cudaFuncSetAttribute (fftconv_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-		attr_done[EPI] = true;
+	static bool attr_done = false; // one flag per template instantiation
+	if (!attr_done) {
+		CK (cudaFuncSetAttribute (fftconv_kernel<EPI, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+		attr_done = true;
 	}
 	const long long total = p.nseg * p.nchan;
 	if (total <= 0) {
 		return PHASEROT_OK;
 	}
 	const int grid = (int)std::min<long long> (total, h->n_sm);
-	fftconv_kernel<EPI><<<grid, kConvThreads, kSmemBytes, h->stream>>> (p);
+	ProfScope ps (h, EPI == EPI_POINTS ? 0 : 3);
+	fftconv_kernel<EPI, SRC><<<grid, kConvThreads, kSmemBytes, h->stream>>> (p);
 	CK (cudaGetLastError ());
 	++h->stats.kernel_launches;
 	return PHASEROT_OK;
@@ -390,6 +439,7 @@ launch_deinterleave (phaserot* h, const float* d_in, long long frame0, long long
 	}
 	const int       nt = 256;
 	const long long nb = (n_count + nt - 1) / nt;
+	ProfScope       ps (h, 2);
 	deinterleave_kernel<<<(unsigned)nb, nt, 0, h->stream>>> (d_in, frame0, n_frames_total, n_first, n_count, h->C,
 	                                                          (float2*)h->d_plane.p, h->plane_stride, h->padf);
 	CK (cudaGetLastError ());
@@ -457,6 +507,7 @@ launch_sweep (phaserot* h, int A, int c0, int nchan)
 	const float2*       cs  = (const float2*)h->d_cs.p;
 	unsigned*           pk  = (unsigned*)h->d_peaks.p;
 	unsigned long long* ne  = d_stats (h) + 1;
+	ProfScope           ps (h, 1);
 	switch (sc.R) {
 		case 1: sweep_kernel<1><<<grid, sc.nt, 0, h->stream>>> (lst, h->list_stride, d_count (h), c0, cs, A, pk, h->pend_A, ne); break;
 		case 2: sweep_kernel<2><<<grid, sc.nt, 0, h->stream>>> (lst, h->list_stride, d_count (h), c0, cs, A, pk, h->pend_A, ne); break;
@@ -487,6 +538,7 @@ finish_pending (phaserot* h)
 	unsigned long long* st = (unsigned long long*)(res + (size_t)A * h->C + (size_t)h->C + (((size_t)A * h->C + h->C) & 1));
 	CK (cudaMemcpyAsync (st, d_stats (h), 2 * sizeof (unsigned long long), cudaMemcpyDeviceToHost, h->stream));
 	CK (cudaStreamSynchronize (h->stream));
+	prof_resolve (h);
 	h->stats.d2h_bytes += bytes;
 	for (int c = h->pend_c0; c < h->pend_c1; ++c) {
 		float* row = h->table.data () + (size_t)c * h->MS;
@@ -502,7 +554,6 @@ finish_pending (phaserot* h)
 			row[0] = std::max (row[0], v);
 		}
 	}
-	h->stats.points_total += st[0];
 	h->stats.points_evaluated += st[1];
 	h->pending = false;
 	return PHASEROT_OK;
@@ -578,11 +629,16 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 	CK (cudaMemsetAsync (h->d_small.p, 0, kSmallBytes, h->stream));
 
 	const long long m_end = (t_end + 1) / 2;
-	long long       nseg  = 0;
-	rc                    = ensure_planes (h, m_end, &nseg);
-	if (rc) return rc;
-	rc = init_front_pad (h, hist);
-	if (rc) return rc;
+	const long long nseg  = (m_end + h->V - 1) / h->V;
+	const float*    d_hist = nullptr;
+	if (hist) {
+		// frames [-L, 0) of the stream, read by the segments that reach before its start
+		rc = h->d_hist.ensure (sizeof (float) * (size_t)h->L * h->C);
+		if (rc) return rc;
+		CK (cudaMemcpyAsync (h->d_hist.p, hist, sizeof (float) * (size_t)h->L * h->C, cudaMemcpyHostToDevice, h->stream));
+		CK (cudaStreamSynchronize (h->stream));
+		d_hist = (const float*)h->d_hist.p;
+	}
 
 	// survivor list: one launch covers at most `segs_max` segments per channel
 	const int       nchan    = c1 - c0;
@@ -599,6 +655,9 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 
 	ConvParams p;
 	fill_conv_common (h, p);
+	p.hist     = d_hist;
+	p.n_frames = n_frames;
+	p.C        = h->C;
 	p.chan0  = c0;
 	p.nchan  = nchan;
 	p.m_end  = m_end;
@@ -609,58 +668,79 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 	p.count       = d_count (h);
 	p.thr2        = d_thr2 (h);
 	p.rawpeak     = d_raw (h);
-	p.n_seen      = d_stats (h);
 	const int thr_mode = A == 0 ? 2 : (h->cfg.flags & PHASEROT_FLAG_NO_PRUNE) ? 0 : 1;
 	threshold_kernel<<<nchan, 32, 0, h->stream>>> ((const unsigned*)h->d_peaks.p, A, A, c0, d_thr2 (h), d_count (h), 1, A == 0 ? 2 : 0);
 	CK (cudaGetLastError ());
 	++h->stats.kernel_launches;
 
-	// complex elements that must be filled: up to nseg * V (zero beyond the data)
-	const long long n_fill  = nseg * h->V;
-	const long long n_data  = (n_frames + 1) / 2; // complex elements that hold data
-	long long       filled  = 0;                  // complex elements deinterleaved so far
-	long long       seg_done = 0;
-	long long       launch_segs = std::max<long long> (1, (h->n_sm + nchan - 1) / nchan);
+	long long       frames_ready = 0; // frames of `inter` that are valid on the device
+	long long       seg_done     = 0;
+	const long long wave     = std::max<long long> (1, (h->n_sm + nchan - 1) / nchan); // segments per channel in one wave
+	bool            booted   = thr_mode != 1;
+
+	// one conv launch + sweep of its survivors + new filter radius
+	auto run_launch = [&] (long long s0, long long stride, long long n) -> int {
+		p.seg0       = s0;
+		p.seg_stride = stride;
+		p.nseg       = n;
+		int r        = launch_conv<EPI_POINTS, SRC_INTER> (h, p);
+		if (r) return r;
+		if (A > 0) {
+			r = launch_sweep (h, A, c0, nchan);
+			if (r) return r;
+		}
+		{
+			ProfScope ps (h, 5);
+			threshold_kernel<<<nchan, 256, 0, h->stream>>> ((const unsigned*)h->d_peaks.p, A, A, c0, d_thr2 (h), d_count (h), 1, thr_mode);
+		}
+		CK (cudaGetLastError ());
+		++h->stats.kernel_launches;
+		return PHASEROT_OK;
+	};
 
 	auto process_ready = [&] (bool final) -> int {
-		const long long seg_ready = final ? nseg : std::min (nseg, filled / h->V);
+		// a segment reads frames below 2 (s + 1) V
+		const long long seg_ready = final ? nseg : std::min (nseg, frames_ready / (2 * (long long)h->V));
+		if (!booted && seg_ready >= 2 * wave) {
+			// Bootstrap the filter radius from a sparse sample of the segments
+			// available so far: a handful first (everything survives, radius 0),
+			// then one wave spread over the range.  The main passes below visit
+			// these segments again, which is harmless for a running maximum.
+			const long long n1 = std::max<long long> (1, 8 / nchan);
+			int r = run_launch (seg_ready / (2 * n1), seg_ready / n1, n1);
+			if (r) return r;
+			r = run_launch (0, seg_ready / wave, wave);
+			if (r) return r;
+			booted = true;
+		}
 		while (seg_done < seg_ready) {
-			long long n = std::min (launch_segs, seg_ready - seg_done);
-			if (!final && n < launch_segs && seg_ready < nseg) {
+			const long long want = booted ? segs_max : wave;
+			const long long n    = std::min (want, seg_ready - seg_done);
+			if (!final && n < want && seg_ready < nseg) {
 				break; // wait for more data to keep launches full
 			}
-			p.seg0 = seg_done;
-			p.nseg = n;
-			int r  = launch_conv<EPI_POINTS> (h, p);
+			const int r = run_launch (seg_done, 1, n);
 			if (r) return r;
-			if (A > 0) {
-				r = launch_sweep (h, A, c0, nchan);
-				if (r) return r;
-			}
-			threshold_kernel<<<nchan, 256, 0, h->stream>>> ((const unsigned*)h->d_peaks.p, A, A, c0, d_thr2 (h), d_count (h), 1, thr_mode);
-			CK (cudaGetLastError ());
-			++h->stats.kernel_launches;
 			seg_done += n;
-			launch_segs = std::min (segs_max, launch_segs * 2);
+			booted = true;
 		}
 		return PHASEROT_OK;
 	};
 
 	if (src_is_device) {
-		rc = launch_deinterleave (h, src, 0, n_frames, 0, n_fill);
-		if (rc) return rc;
-		filled = n_fill;
-		rc     = process_ready (true);
+		p.inter      = src;
+		frames_ready = n_frames;
+		rc           = process_ready (true);
 		if (rc) return rc;
 	} else {
-		// double-buffered H2D on the copy stream, compute on the main stream
+		// H2D in chunks on the copy stream straight into the device copy of the
+		// file; the compute stream starts on a chunk as soon as it has landed
+		rc = h->d_inter.ensure (std::max<size_t> (sizeof (float) * (size_t)n_frames * h->C, 16));
+		if (rc) return rc;
+		p.inter = (const float*)h->d_inter.p;
 		const long long chunk_frames = std::max<long long> (2, ((8LL << 20) / h->C) & ~1LL); // ~32 MB per chunk
-		for (int b = 0; b < 2; ++b) {
-			rc = h->d_stage[b].ensure (sizeof (float) * (size_t)chunk_frames * h->C);
-			if (rc) return rc;
-		}
 		cudaPointerAttributes at;
-		bool pinned = (cudaPointerGetAttributes (&at, src) == cudaSuccess) && (at.type == cudaMemoryTypeHost);
+		const bool pinned = (cudaPointerGetAttributes (&at, src) == cudaSuccess) && (at.type == cudaMemoryTypeHost);
 		cudaGetLastError ();
 		if (!pinned) {
 			for (int b = 0; b < 2; ++b) {
@@ -668,53 +748,40 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 				if (rc) return rc;
 			}
 		}
+		// the previous pass may still be reading d_inter on the compute stream
+		CK (cudaEventRecord (h->ev_done[0], h->stream));
+		CK (cudaStreamWaitEvent (h->copy_stream, h->ev_done[0], 0));
 		int       b  = 0;
 		long long f0 = 0;
 		bool      used[2] = { false, false };
 		while (f0 < n_frames) {
 			const long long nf    = std::min (chunk_frames, n_frames - f0);
 			const size_t    bytes = sizeof (float) * (size_t)nf * h->C;
-			if (used[b]) {
-				CK (cudaStreamWaitEvent (h->copy_stream, h->ev_done[b], 0)); // staging buffer free again
-			}
-			const float* hsrc = src + (size_t)f0 * h->C;
+			const float*    hsrc  = src + (size_t)f0 * h->C;
 			if (!pinned) {
 				if (used[b]) {
-					CK (cudaEventSynchronize (h->ev_copy[b]));
+					CK (cudaEventSynchronize (h->ev_copy[b])); // staging buffer free again
 				}
 				memcpy (h->h_stage[b].p, hsrc, bytes);
 				hsrc = (const float*)h->h_stage[b].p;
 			}
-			CK (cudaMemcpyAsync (h->d_stage[b].p, hsrc, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+			CK (cudaMemcpyAsync ((float*)h->d_inter.p + (size_t)f0 * h->C, hsrc, bytes, cudaMemcpyHostToDevice, h->copy_stream));
 			CK (cudaEventRecord (h->ev_copy[b], h->copy_stream));
 			CK (cudaStreamWaitEvent (h->stream, h->ev_copy[b], 0));
 			h->stats.h2d_bytes += bytes;
-			const long long n_first = f0 / 2;
-			const long long n_cnt   = (f0 + nf + 1) / 2 - n_first;
-			rc = launch_deinterleave (h, (const float*)h->d_stage[b].p, f0, n_frames, n_first, n_cnt);
-			if (rc) return rc;
-			CK (cudaEventRecord (h->ev_done[b], h->stream));
 			used[b] = true;
-			filled  = n_first + n_cnt;
 			f0 += nf;
+			frames_ready = f0;
 			if (f0 < n_frames) {
-				// only whole elements strictly inside the data are final
-				filled = f0 / 2;
-				rc     = process_ready (false);
+				rc = process_ready (false);
 				if (rc) return rc;
 			}
 			b ^= 1;
 		}
-		// zero tail beyond the data
-		if (n_fill > n_data) {
-			for (int c = 0; c < h->C; ++c) {
-				CK (cudaMemsetAsync ((float2*)h->d_plane.p + (long long)c * h->plane_stride + h->padf + n_data, 0,
-				                     sizeof (float2) * (size_t)(n_fill - n_data), h->stream));
-			}
-		}
 		rc = process_ready (true);
 		if (rc) return rc;
 	}
+	h->stats.points_total += (uint64_t)nchan * (uint64_t)(2 * (m_end - p.m_skip));
 	h->pending = true;
 	return PHASEROT_OK;
 }
@@ -790,6 +857,7 @@ launch_interleave (phaserot* h, long long m_count, long long m_first, float* d_d
 	}
 	const int       nt = 256;
 	const long long nb = (m_count + nt - 1) / nt;
+	ProfScope       ps (h, 2);
 	interleave_kernel<<<(unsigned)nb, nt, 0, h->stream>>> ((const float2*)h->d_out.p + m_first, h->out_stride, h->C, m_count, d_dst, n_frames_out);
 	CK (cudaGetLastError ());
 	++h->stats.kernel_launches;
@@ -1063,7 +1131,7 @@ phaserot_destroy (phaserot_t* h)
 	DevGuard                    guard (h->dev);
 	if (h->own_stream) cudaStreamSynchronize (h->own_stream);
 	if (h->copy_stream) cudaStreamSynchronize (h->copy_stream);
-	for (DevBuf* b : { &h->d_G, &h->d_tw, &h->d_g, &h->d_plane, &h->d_out, &h->d_list, &h->d_stage[0], &h->d_stage[1], &h->d_io, &h->d_small,
+	for (DevBuf* b : { &h->d_G, &h->d_tw, &h->d_g, &h->d_plane, &h->d_out, &h->d_list, &h->d_stage[0], &h->d_stage[1], &h->d_io, &h->d_inter, &h->d_hist, &h->d_small,
 	                   &h->d_cs, &h->d_peaks, &h->d_ramp, &h->d_chancs }) {
 		b->release ();
 	}
@@ -1074,6 +1142,7 @@ phaserot_destroy (phaserot_t* h)
 		if (h->ev_copy[b]) cudaEventDestroy (h->ev_copy[b]);
 		if (h->ev_done[b]) cudaEventDestroy (h->ev_done[b]);
 	}
+	for (cudaEvent_t e : h->prof_ev) cudaEventDestroy (e);
 	if (h->own_stream) cudaStreamDestroy (h->own_stream);
 	if (h->copy_stream) cudaStreamDestroy (h->copy_stream);
 	delete h;
@@ -1201,7 +1270,55 @@ phaserot_sync (phaserot_t* h)
 	rc = finish_pending (h);
 	if (rc) return rc;
 	CK (cudaStreamSynchronize (h->stream));
+	prof_resolve (h);
 	return PHASEROT_OK;
+}
+
+int
+phaserot_set_profiling (phaserot_t* h, int on)
+{
+	if (!h) {
+		return PHASEROT_E_INVAL;
+	}
+	DevGuard guard (h->dev);
+	CK (cudaStreamSynchronize (h->stream));
+	prof_resolve (h);
+	h->prof = on != 0;
+	memset (&h->ktimes, 0, sizeof (h->ktimes));
+	return PHASEROT_OK;
+}
+
+int
+phaserot_get_kernel_times (phaserot_t* h, phaserot_ktimes_t* out)
+{
+	if (!h || !out) {
+		return PHASEROT_E_INVAL;
+	}
+	DevGuard guard (h->dev);
+	CK (cudaStreamSynchronize (h->stream));
+	prof_resolve (h);
+	*out = h->ktimes;
+	return PHASEROT_OK;
+}
+
+int
+phaserot_sweep_shard_device (phaserot_t* h, const float* d_interleaved, uint64_t n_frames, const float* hist, int first, int last,
+                             int ang_start, int ang_end, int ang_stride, int chn)
+{
+	if (!h || (!d_interleaved && n_frames)) {
+		return PHASEROT_E_INVAL;
+	}
+	if (h->plugin) {
+		return PHASEROT_E_STATE;
+	}
+	const long long F = (long long)n_frames;
+	if (!last && (F % h->L) != 0) {
+		return PHASEROT_E_INVAL;
+	}
+	DevGuard        guard (h->dev);
+	const long long B     = (F + h->L - 1) / h->L;
+	const long long t_end = last ? (B + 1) * h->L : F;
+	return sweep_core (h, d_interleaved, true, F, t_end, first != 0 && B > 0, hist, ang_start, ang_end, ang_stride, chn);
 }
 
 float
@@ -1304,6 +1421,16 @@ render_bulk (phaserot* h, const float* src, bool dev_in, uint64_t n_frames, cons
 	long long m_end = 0;
 	int       rc    = render_core (h, src, dev_in, F, t_end, nullptr, cs.data (), nullptr, 0, nullptr, &m_end);
 	if (rc) return rc;
+	// stream state for a following apply(): the last block that went in
+	std::fill (h->ap_hist.begin (), h->ap_hist.end (), 0.f);
+	if (flush_blocks == 0 && B > 0 && !dev_in) {
+		const long long f0 = (B - 1) * h->L;
+		memcpy (h->ap_hist.data (), src + (size_t)f0 * h->C, sizeof (float) * (size_t)(F - f0) * h->C);
+	} else if (flush_blocks == 0 && B > 0 && dev_in) {
+		const long long f0 = (B - 1) * h->L;
+		CK (cudaMemcpyAsync (h->ap_hist.data (), src + (size_t)f0 * h->C, sizeof (float) * (size_t)(F - f0) * h->C, cudaMemcpyDeviceToHost, h->stream));
+		CK (cudaStreamSynchronize (h->stream));
+	}
 	if (dev_out) {
 		return launch_interleave (h, m_end, 0, dst, t_end);
 	}
@@ -1329,6 +1456,20 @@ int
 phaserot_render_device (phaserot_t* h, const float* d_interleaved, uint64_t n_frames, const int* angles, int flush_blocks, float* d_out)
 {
 	return render_bulk (h, d_interleaved, true, n_frames, angles, flush_blocks, d_out, true);
+}
+
+uint32_t
+phaserot_shard_align (const phaserot_t* h)
+{
+	if (!h || h->plugin) {
+		return 0;
+	}
+	// one FFT segment yields 2 V samples; 2 V = 32768 - L is a multiple of L for every power-of-two L
+	uint32_t a = 2u * (uint32_t)h->V;
+	while (a % (uint32_t)h->L) {
+		a += 2u * (uint32_t)h->V;
+	}
+	return a;
 }
 
 uint32_t
@@ -1444,6 +1585,7 @@ phaserot_process (phaserot_t* h, const float* const* in, float* const* out, uint
 			fc.rlen[c] = ramp_len[c < C ? c : 0];
 		}
 		const dim3 grid ((n + 127) / 128, (unsigned)C);
+		ProfScope  ps (h, 4);
 		fir_direct_kernel<<<grid, 128, smem, h->stream>>> (dW, (int)wstride, (int)wlen, (long long)wlen, (long long)firlen, (int)n,
 		                                                    (const float*)h->d_g.p, nodd, (int)h->firlat, dpre, (int)pre_cap, fc, dy, (int)n);
 		CK (cudaGetLastError ());
@@ -1527,6 +1669,25 @@ phaserot_process (phaserot_t* h, const float* const* in, float* const* out, uint
 		h->stats.d2h_bytes += sizeof (float) * (size_t)n * C;
 	}
 	return PHASEROT_OK;
+}
+
+void*
+phaserot_alloc_host (uint64_t bytes)
+{
+	void* p = nullptr;
+	if (cudaHostAlloc (&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+		cudaGetLastError ();
+		return nullptr;
+	}
+	return p;
+}
+
+void
+phaserot_free_host (void* p)
+{
+	if (p) {
+		cudaFreeHost (p);
+	}
 }
 
 int

@@ -216,6 +216,26 @@ def two_sine(sr, seconds, channels=2):
     return np.stack(chans, 1).astype(np.float32)
 
 
+def harmonic(sr, seconds, channels=2, seed=5):
+    """Harmonic-rich, asymmetric waveforms (band-limited saw / pulse-like sums with
+    random start phases): the peak depends strongly on the rotation angle and has
+    one clear minimum per channel, so angle selection is not decided by rounding."""
+    rng = np.random.default_rng(seed)
+    n = int(sr * seconds)
+    t = np.arange(n, dtype=np.float64) / sr
+    out = []
+    for c in range(channels):
+        f0 = [110.3, 82.4, 146.9, 65.4, 98.1, 123.5, 73.4, 55.2][c % 8]
+        skew = rng.uniform(0.2, 1.2)
+        y = np.zeros(n)
+        for k in range(1, 13):
+            y += (1.0 / k) * np.sin(2 * np.pi * k * f0 * t + skew * k + 0.1 * c)
+        y *= 0.8 / np.max(np.abs(y))
+        y += 0.01 * rng.standard_normal(n)
+        out.append(y)
+    return np.stack(out, 1).astype(np.float32)
+
+
 def pink_noise(n, seed=42, peak=0.5):
     """Paul Kellet's economy pink filter over seeded uniform noise, peak normalised."""
     rng = np.random.default_rng(seed)
