@@ -250,15 +250,25 @@ rotated_peak (const float* b0, const float* b1, int64_t n, float pk, float sa, f
  *     i.e. against all-zero history (cli:418-419);
  *   - otherwise max_i |ca * x[t0 + i - L/2] + sa * H[t0 + i]|, i in [0, L) (cli:421).
  */
+/*
+ * Shard form used by the multi-GPU tests: the stream continues a longer one.
+ *   hist  : blksiz frames (interleaved) that precede `interleaved`, or NULL (silence)
+ *   first : the shard starts the stream -> first-block rule applies to its block 0
+ *   last  : the shard ends the stream  -> short block zero padded + zero flush block;
+ *           otherwise n_frames must be a multiple of blksiz and no flush block is run
+ * pro_cli_analyze() is the whole-file case (hist NULL, first = last = 1).
+ */
 void
-pro_cli_analyze (const float* interleaved, int64_t n_frames, int n_chn, int blksiz, int subsample,
-                 int ang_start, int ang_end, int ang_stride, int only_chn, float* peaks)
+pro_cli_analyze_shard (const float* interleaved, int64_t n_frames, int n_chn, int blksiz, int subsample,
+                       const float* hist, int first, int last,
+                       int ang_start, int ang_end, int ang_stride, int only_chn, float* peaks)
 {
 	const int     L         = blksiz;
 	const int     D         = L / 2;
 	const int     maxsample = 180 * subsample;
-	const int64_t B         = (n_frames + L - 1) / L;
-	const int64_t n_pad     = (B + 1) * (int64_t)L; /* real blocks + flush block */
+	const int64_t B         = last ? (n_frames + L - 1) / L : n_frames / L;
+	const int64_t n_blocks  = last ? B + 1 : B; /* real blocks (+ flush block) */
+	const int64_t n_pad     = n_blocks * (int64_t)L;
 
 	float* lut_s = (float*)malloc (sizeof (float) * (size_t)maxsample);
 	float* lut_c = (float*)malloc (sizeof (float) * (size_t)maxsample);
@@ -266,32 +276,37 @@ pro_cli_analyze (const float* interleaved, int64_t n_frames, int n_chn, int blks
 	pro_sincos_lut (subsample, lut_s, lut_c);
 	pro_fir_taps (L, taps);
 
-	/* x with one block of zero history in front: xz[L + t] = x[t] */
+	/* x with one block of history in front: xz[L + t] = x[t] */
 	float* xz = (float*)calloc ((size_t)(n_pad + L), sizeof (float));
-	float* H  = (float*)malloc (sizeof (float) * (size_t)n_pad);
+	float* H  = (float*)malloc (sizeof (float) * (size_t)(n_pad + L));
 
 	const int c0 = only_chn < 0 ? 0 : only_chn;
 	const int c1 = only_chn < 0 ? n_chn : only_chn + 1;
 
 	for (int c = c0; c < c1; ++c) {
+		for (int i = 0; i < L; ++i) {
+			xz[i] = hist ? hist[(size_t)i * n_chn + c] : 0.f;
+		}
 		for (int64_t t = 0; t < n_frames; ++t) {
 			xz[L + t] = interleaved[t * n_chn + c];
 		}
-		pro_hilbert_fir (xz + L, n_frames, taps, L, H, n_pad);
+		/* convolve from the start of the history so that H over the shard sees it;
+		 * H[L + t] is the value at shard time t */
+		pro_hilbert_fir (xz, n_frames + L, taps, L, H, n_pad + L);
 		float* pk = peaks + (size_t)c * maxsample;
 
-		for (int64_t n = 0; n <= B; ++n) {
-			const int     start = (n == 0 && B > 0);
+		for (int64_t n = 0; n < n_blocks; ++n) {
+			const int     start = (first && n == 0 && B > 0);
 			const float*  blk   = xz + L + n * (int64_t)L; /* new block */
 			const float*  dly   = blk - D;                /* &tdc[firlen] */
-			const float*  hil   = H + n * (int64_t)L;
+			const float*  hil   = H + L + n * (int64_t)L;
 			int           angle = ang_start;
 			while (angle <= ang_end) {
 				const int a = ((angle % maxsample) + maxsample) % maxsample;
 				if (angle == 0) {
 					pk[a] = peak_abs (blk, L, pk[a]);
 				} else if (start) {
-					/* history is all zero here by construction (xz prefix) */
+					/* history is all zero here (start of the stream) */
 					pk[a] = rotated_peak (dly, hil + D, D, pk[a], lut_s[a], lut_c[a]);
 				} else {
 					pk[a] = rotated_peak (dly, hil, L, pk[a], lut_s[a], lut_c[a]);
@@ -308,6 +323,13 @@ pro_cli_analyze (const float* interleaved, int64_t n_frames, int n_chn, int blks
 	free (taps);
 	free (lut_c);
 	free (lut_s);
+}
+
+void
+pro_cli_analyze (const float* interleaved, int64_t n_frames, int n_chn, int blksiz, int subsample,
+                 int ang_start, int ang_end, int ang_stride, int only_chn, float* peaks)
+{
+	pro_cli_analyze_shard (interleaved, n_frames, n_chn, blksiz, subsample, NULL, 1, 1, ang_start, ang_end, ang_stride, only_chn, peaks);
 }
 
 /* ------------------------------------------------------------------------- */
