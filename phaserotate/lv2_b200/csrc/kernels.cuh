@@ -26,13 +26,13 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "fft16k.cuh"
+#include "tmem_stash.cuh"
+
 namespace prk {
 
-constexpr int kLog2M   = 14;
-constexpr int kM       = 1 << kLog2M; // complex FFT size per segment
-constexpr int kConvThreads = 512;
-constexpr int kSmemElems   = kM + (kM >> 6) * 4; // padded: 4 extra float2 per 64
-constexpr int kSmemBytes   = kSmemElems * (int)sizeof (float2);
+constexpr int kXchFloats = 16 * 32;                                   // Im of lane 31's outputs, per warp
+constexpr int kSmemBytes = kM * (int)sizeof (float2) + (kXchFloats + 4 + kConvThreads) * (int)sizeof (float); // + TMEM base address slot + thread ids
 
 enum { EPI_POINTS = 0, EPI_RENDER = 1, EPI_HILBERT = 2 };
 
@@ -46,10 +46,9 @@ struct ConvParams {
 	const float*  hist;         // SRC_INTER: interleaved frames [-2 Lh, 0) preceding the stream, or nullptr (silence)
 	long long     n_frames;     // SRC_INTER: frames present in `inter`
 	int           C;            // SRC_INTER: channels per frame
-	const float2* G;            // [kM] filter spectrum / kM, in the forward pass's output order
-	const float2* tw1;          // [6][1024]  W_M^(j q),    q in {1,2,3,4,8,12}
-	const float2* tw2;          // [6][64]    W_1024^(j q)
-	const float2* tw3;          // [6][4]     W_64^(j q)
+	const float2* G;            // [kM] filter spectrum / kM in MID-pass order (fft16k_tables.h)
+	const float2* tw1;          // [10][512]  W_M^(e a), a = 1..7 | W_M^(8 e b), b = 1..3
+	const float2* tw2;          // [15][32]   W_512^(j q2), j = 1..15
 	int           Lh;           // half taps = L/2 (multiple of 4)
 	int           V;            // valid complex outputs per segment = kM - Lh
 	int           chan0;        // first channel of this launch
@@ -75,139 +74,46 @@ struct ConvParams {
 	const int*    ramp_len;     // [n_chan] (in samples, even) or nullptr
 };
 
-// ---------------------------------------------------------------------------
-// small complex helpers
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ float2 cadd (float2 a, float2 b) { return make_float2 (a.x + b.x, a.y + b.y); }
-__device__ __forceinline__ float2 csub (float2 a, float2 b) { return make_float2 (a.x - b.x, a.y - b.y); }
-__device__ __forceinline__ float2 cmul (float2 a, float2 b)
-{
-	return make_float2 (fmaf (a.x, b.x, -a.y * b.y), fmaf (a.x, b.y, a.y * b.x));
-}
-// a * conj(b)
-__device__ __forceinline__ float2 cmulc (float2 a, float2 b)
-{
-	return make_float2 (fmaf (a.x, b.x, a.y * b.y), fmaf (a.y, b.x, -a.x * b.y));
-}
-// multiply by the primitive 4th root used in direction DIR: -i (forward) or +i (inverse)
-template <int DIR>
-__device__ __forceinline__ float2 mulw4 (float2 a)
-{
-	return DIR < 0 ? make_float2 (a.y, -a.x) : make_float2 (-a.y, a.x);
-}
-
-template <int DIR>
-__device__ __forceinline__ void dft4 (float2& a0, float2& a1, float2& a2, float2& a3)
-{
-	const float2 s02 = cadd (a0, a2), d02 = csub (a0, a2);
-	const float2 s13 = cadd (a1, a3), d13 = mulw4<DIR> (csub (a1, a3));
-	a0 = cadd (s02, s13);
-	a2 = csub (s02, s13);
-	a1 = cadd (d02, d13);
-	a3 = csub (d02, d13);
-}
-
-// multiply by exp(DIR * 2 pi i m / 16), m compile-time
-template <int DIR, int m>
-__device__ __forceinline__ float2 mulw16 (float2 a)
-{
-	constexpr float C1 = 0.92387953251128675613f; // cos(pi/8)
-	constexpr float S1 = 0.38268343236508977173f; // sin(pi/8)
-	constexpr float H  = 0.70710678118654752440f;
-	constexpr float sg = DIR < 0 ? -1.f : 1.f;
-	if (m == 0) return a;
-	if (m == 1) return make_float2 (a.x * C1 - a.y * (sg * S1), a.x * (sg * S1) + a.y * C1);
-	if (m == 2) return make_float2 ((a.x - sg * a.y) * H, (sg * a.x + a.y) * H);
-	if (m == 3) return make_float2 (a.x * S1 - a.y * (sg * C1), a.x * (sg * C1) + a.y * S1);
-	if (m == 4) return mulw4<DIR> (a);
-	if (m == 6) return make_float2 ((-a.x - sg * a.y) * H, (sg * a.x - a.y) * H);
-	if (m == 9) return make_float2 (-a.x * C1 + a.y * (sg * S1), -a.x * (sg * S1) - a.y * C1);
-	return a;
-}
-
-// 16-point DFT in registers.  Input u[k] natural order; on return the value
-// y[q] sits in u[(q >> 2) + 4 * (q & 3)].
-template <int DIR>
-__device__ __forceinline__ void dft16 (float2 (&u)[16])
-{
-#pragma unroll
-	for (int k0 = 0; k0 < 4; ++k0) {
-		dft4<DIR> (u[k0], u[k0 + 4], u[k0 + 8], u[k0 + 12]); // u[k0 + 4 ql] = v[k0][ql]
-	}
-	u[5]  = mulw16<DIR, 1> (u[5]);
-	u[9]  = mulw16<DIR, 2> (u[9]);
-	u[13] = mulw16<DIR, 3> (u[13]);
-	u[6]  = mulw16<DIR, 2> (u[6]);
-	u[10] = mulw16<DIR, 4> (u[10]);
-	u[14] = mulw16<DIR, 6> (u[14]);
-	u[7]  = mulw16<DIR, 3> (u[7]);
-	u[11] = mulw16<DIR, 6> (u[11]);
-	u[15] = mulw16<DIR, 9> (u[15]);
-#pragma unroll
-	for (int ql = 0; ql < 4; ++ql) {
-		dft4<DIR> (u[4 * ql], u[4 * ql + 1], u[4 * ql + 2], u[4 * ql + 3]); // u[qh + 4 ql] = y[4 qh + ql]
-	}
-}
-
-__device__ __forceinline__ int phys (int i) { return i + ((i >> 6) << 2); }
-
-// The 15 inter-pass twiddles W^(j q), q = ql + 4 qh, from six table entries.
-struct Tw6 {
-	float2 t1, t2, t3, t4, t8, t12;
-};
-__device__ __forceinline__ Tw6 load_tw (const float2* __restrict__ tw, int stride, int j)
-{
-	Tw6 t;
-	t.t1  = __ldg (tw + j);
-	t.t2  = __ldg (tw + stride + j);
-	t.t3  = __ldg (tw + 2 * stride + j);
-	t.t4  = __ldg (tw + 3 * stride + j);
-	t.t8  = __ldg (tw + 4 * stride + j);
-	t.t12 = __ldg (tw + 5 * stride + j);
-	return t;
-}
-template <bool CONJ>
-__device__ __forceinline__ float2 apply_tw (float2 v, const Tw6& t, int q)
-{
-	const int ql = q & 3, qh = q >> 2;
-	if (ql) {
-		const float2 a = ql == 1 ? t.t1 : ql == 2 ? t.t2 : t.t3;
-		v              = CONJ ? cmulc (v, a) : cmul (v, a);
-	}
-	if (qh) {
-		const float2 b = qh == 1 ? t.t4 : qh == 2 ? t.t8 : t.t12;
-		v              = CONJ ? cmulc (v, b) : cmul (v, b);
-	}
-	return v;
-}
-
 // Segment input loaders: z[n0 + idx] for the first forward pass and the direct
-// branch of the epilogue.
+// branch of the epilogue.  `thread (e)` binds the per-thread part of the address
+// once; the returned object is then indexed with compile-time offsets (512 k),
+// which become immediate offsets of the load instructions.
 struct PlaneLoader { // planar float2 stream
 	const float2* src;
-	__device__ __forceinline__ float2 operator() (int idx) const { return __ldg (src + idx); }
+	struct T {
+		const float2* p;
+		__device__ __forceinline__ float2 operator() (int off) const { return __ldg (p + off); }
+	};
+	__device__ __forceinline__ T thread (int e) const { return T { src + e }; }
 };
-struct Inter1Loader { // mono: the interleaved stream is the plane
-	const float2* src;
-	__device__ __forceinline__ float2 operator() (int idx) const { return __ldg (src + idx); }
-};
+typedef PlaneLoader Inter1Loader; // mono: the interleaved stream is the plane
 struct Inter2Loader { // stereo: one 16 byte load = frames 2n, 2n+1 of both channels
 	const float4* src;
 	int           chan;
-	__device__ __forceinline__ float2 operator() (int idx) const
-	{
-		const float4 v = __ldg (src + idx);
-		return chan ? make_float2 (v.y, v.w) : make_float2 (v.x, v.z);
-	}
+	struct T {
+		const float4* p;
+		int           chan;
+		__device__ __forceinline__ float2 operator() (int off) const
+		{
+			const float4 v = __ldg (p + off);
+			return chan ? make_float2 (v.y, v.w) : make_float2 (v.x, v.z);
+		}
+	};
+	__device__ __forceinline__ T thread (int e) const { return T { src + e, chan }; }
 };
 struct InterNLoader { // any channel count, two scalar loads
 	const float* src; // &inter[(2 n0) * C + c]
 	int          C;
-	__device__ __forceinline__ float2 operator() (int idx) const
-	{
-		const float* a = src + (long long)(2 * idx) * C;
-		return make_float2 (__ldg (a), __ldg (a + C));
-	}
+	struct T {
+		const float* p;
+		int          C;
+		__device__ __forceinline__ float2 operator() (int off) const
+		{
+			const float* a = p + (long long)(2 * off) * C;
+			return make_float2 (__ldg (a), __ldg (a + C));
+		}
+	};
+	__device__ __forceinline__ T thread (int e) const { return T { src + (long long)(2 * e) * C, C }; }
 };
 struct EdgeLoader { // segments that touch the stream start (history / silence) or its end (zero padding)
 	const float* inter;
@@ -219,94 +125,17 @@ struct EdgeLoader { // segments that touch the stream start (history / silence) 
 		if (f >= 0) return f < n_frames ? __ldg (inter + f * C + c) : 0.f;
 		return (hist && f >= -(long long)L) ? __ldg (hist + (L + f) * C + c) : 0.f;
 	}
-	__device__ __forceinline__ float2 operator() (int idx) const
-	{
-		const long long f = f0 + 2 * (long long)idx;
-		return make_float2 (at (f), at (f + 1));
-	}
+	struct T {
+		const EdgeLoader* l;
+		int               e;
+		__device__ __forceinline__ float2 operator() (int off) const
+		{
+			const long long f = l->f0 + 2 * (long long)(e + off);
+			return make_float2 (l->at (f), l->at (f + 1));
+		}
+	};
+	__device__ __forceinline__ T thread (int e) const { return T { this, e }; }
 };
-
-// One radix-16 pass over the whole segment held in shared memory.
-// Butterfly e: block = e / STRIDE (size 16 * STRIDE), j = e % STRIDE.
-// Forward (DIF): u = data[j + k STRIDE]; y = DFT16(u); store y[q] * W^(j q) at q.
-// Inverse (DIT): y[q] * conj W^(j q); u = IDFT16; store u[k] at k.
-struct NoLoader {
-	__device__ __forceinline__ float2 operator() (int) const { return make_float2 (0.f, 0.f); }
-};
-
-template <int DIR, int STRIDE, bool FROM_GLOBAL, class Loader = NoLoader>
-__device__ __forceinline__ void pass16 (float2* sm, const float2* __restrict__ tw, int tid, const Loader ld = Loader ())
-{
-	// padded distance between two inputs of one butterfly (see phys())
-	constexpr int PS = STRIDE >= 64 ? STRIDE + STRIDE / 16 : STRIDE;
-#pragma unroll 1
-	for (int e = tid; e < kM / 16; e += kConvThreads) {
-		const int blk  = e / STRIDE;
-		const int j    = e - blk * STRIDE;
-		const int base = blk * (16 * STRIDE) + j;
-		float2*   sp   = sm + phys (base);
-		float2    u[16];
-		if (FROM_GLOBAL) {
-#pragma unroll
-			for (int k = 0; k < 16; ++k) {
-				u[k] = ld (base + k * STRIDE);
-			}
-		} else {
-#pragma unroll
-			for (int k = 0; k < 16; ++k) {
-				u[k] = sp[k * PS];
-			}
-		}
-		const Tw6 t = load_tw (tw, STRIDE, j);
-		if (DIR > 0) {
-#pragma unroll
-			for (int q = 1; q < 16; ++q) {
-				u[q] = apply_tw<true> (u[q], t, q);
-			}
-		}
-		dft16<DIR> (u);
-#pragma unroll
-		for (int q = 0; q < 16; ++q) {
-			float2 v = u[(q >> 2) + 4 * (q & 3)];
-			if (DIR < 0 && q) {
-				v = apply_tw<false> (v, t, q);
-			}
-			sp[q * PS] = v;
-		}
-	}
-}
-
-// Innermost radix-4 forward pass, spectrum multiply, radix-4 inverse pass, all
-// on the same four shared-memory elements.
-__device__ __forceinline__ void mid_pass (float2* sm, const float2* __restrict__ G, int tid)
-{
-	const float4* G4 = reinterpret_cast<const float4*> (G);
-	constexpr int kIter = kM / 4 / kConvThreads;
-	float4 g0 = __ldg (G4 + 2 * tid), g1 = __ldg (G4 + 2 * tid + 1);
-#pragma unroll
-	for (int it = 0; it < kIter; ++it) {
-		const int e  = tid + it * kConvThreads;
-		float4    n0 = g0, n1 = g1;
-		if (it + 1 < kIter) { // next iteration's spectrum values are in flight while this one computes
-			n0 = __ldg (G4 + 2 * (e + kConvThreads));
-			n1 = __ldg (G4 + 2 * (e + kConvThreads) + 1);
-		}
-		float4* p  = reinterpret_cast<float4*> (sm + phys (4 * e));
-		float4  v0 = p[0], v1 = p[1];
-		float2  a0 = make_float2 (v0.x, v0.y), a1 = make_float2 (v0.z, v0.w);
-		float2  a2 = make_float2 (v1.x, v1.y), a3 = make_float2 (v1.z, v1.w);
-		dft4<-1> (a0, a1, a2, a3);
-		a0 = cmul (a0, make_float2 (g0.x, g0.y));
-		a1 = cmul (a1, make_float2 (g0.z, g0.w));
-		a2 = cmul (a2, make_float2 (g1.x, g1.y));
-		a3 = cmul (a3, make_float2 (g1.z, g1.w));
-		dft4<+1> (a0, a1, a2, a3);
-		p[0] = make_float4 (a0.x, a0.y, a1.x, a1.y);
-		p[1] = make_float4 (a2.x, a2.y, a3.x, a3.y);
-		g0   = n0;
-		g1   = n1;
-	}
-}
 
 __device__ __forceinline__ unsigned lanemask_lt ()
 {
@@ -334,27 +163,6 @@ __device__ __forceinline__ void append_points (float2* lst, unsigned* cnt, bool 
 	}
 }
 
-// Forward passes, spectrum multiply and inverse passes of one segment; the
-// first pass pulls its input through `ld`.
-template <class Loader>
-__device__ __forceinline__ void transform_segment (float2* sm, const ConvParams& p, int tid, const Loader ld)
-{
-	pass16<-1, 1024, true> (sm, p.tw1, tid, ld);
-	__syncthreads ();
-	pass16<-1, 64, false> (sm, p.tw2, tid);
-	__syncthreads ();
-	pass16<-1, 4, false> (sm, p.tw3, tid);
-	__syncthreads ();
-	mid_pass (sm, p.G, tid);
-	__syncthreads ();
-	pass16<+1, 4, false> (sm, p.tw3, tid);
-	__syncthreads ();
-	pass16<+1, 64, false> (sm, p.tw2, tid);
-	__syncthreads ();
-	pass16<+1, 1024, false> (sm, p.tw1, tid);
-	__syncthreads ();
-}
-
 // Epilogue state shared by the loader-specific instantiations.
 struct EpiCtx {
 	int       c, i_hi, i_skip, i_zero;
@@ -362,56 +170,106 @@ struct EpiCtx {
 	float     rawmax;
 };
 
-// Epilogue over the valid outputs: local index i in [Lh, M), complex index m = mbase + i.
+// Epilogue straight from the registers of the last inverse pass: thread e holds
+// the outputs w[k] of local index i = e + 512 k; valid ones have i in [Lh, i_hi),
+// complex index m = mbase + i.
 //   H[2m] = Im w[m-1], H[2m+1] = Re w[m];  direct branch x_d pair = z[m - Lh/2] = ld (i - Lh/2).
-template <int EPI, class Loader>
-__device__ __forceinline__ void epilogue (float2* sm, const ConvParams& p, int tid, int lane, EpiCtx& cx, const Loader ld)
+// Im w[i-1] comes from the neighbouring lane (shuffle), for lane 0 from the
+// previous warp through `xch` (written by every lane 31 before the barrier).
+struct TmemStash {
+	uint32_t tb;
+	__device__ __forceinline__ void operator() (int k, float2 a, float2 b, float2 c, float2 d) const { tmem_st4 (tb + 2 * k, a, b, c, d); }
+};
+
+// The stash serves the epilogue when the delay Lh/2 is a multiple of 2048 points:
+// output block kb .. kb + 3 then needs the aligned input block kb - Lh/1024 of
+// the same thread (Lh = 4096 and 8192, i.e. the CLI block sizes 8192 and 16384).
+__device__ __forceinline__ bool stash_usable (int dl) { return (dl & 2047) == 0; }
+
+// The direct-branch inputs of outputs k .. k + 3: from the TMEM stash when the
+// delay Lh/2 is a whole number of 512-point strides (then they are inputs
+// k - Lh/1024 .. of the same thread), else re-read through the loader.
+template <class Loader>
+__device__ __forceinline__ void load_direct (float2 (&zd)[4], const bool (&ok)[4], int tid, int kb, int dl, uint32_t tb, const Loader& ld)
 {
-	const int dl = p.Lh >> 1;
+	if (stash_usable (dl)) {
+		tmem_ld4 (tb + 2 * (kb - (dl >> 9)), zd);
+	} else {
+		const auto lt = ld.thread (tid - dl);
+#pragma unroll
+		for (int kk = 0; kk < 4; ++kk) zd[kk] = ok[kk] ? lt (512 * (kb + kk)) : make_float2 (0.f, 0.f);
+	}
+}
+
+template <int EPI, class Loader>
+__device__ __forceinline__ void epilogue (const float2 (&w)[32], const float* xch, uint32_t tb, const ConvParams& p, int tid, int lane, EpiCtx& cx, const Loader& ld)
+{
+	const int dl    = p.Lh >> 1;
+	const int warp  = tid >> 5;
+	const int xbase = warp ? (warp - 1) * 32 : 15 * 32 - 1;
 	if (EPI == EPI_POINTS) {
-		const float    thr2 = p.thr2[cx.c];
-		float2*        lst  = p.list + (long long)cx.c * p.list_stride;
-		unsigned*      cnt  = p.count + cx.c;
-		const unsigned lt   = lanemask_lt ();
+		const float    thr2   = p.thr2[cx.c];
+		float2*        lst    = p.list + (long long)cx.c * p.list_stride;
+		unsigned*      cnt    = p.count + cx.c;
+		const unsigned lt     = lanemask_lt ();
 		float          rawmax = cx.rawmax;
-		const bool interior = (cx.i_hi == kM) && (cx.i_skip == p.Lh) && (cx.i_zero == p.Lh);
+		// interior segment whose valid region starts on a block of four strides:
+		// no bounds logic, the direct branch comes from the TMEM stash
+		const bool interior = cx.i_hi == kM && cx.i_skip == p.Lh && cx.i_zero == p.Lh && stash_usable (dl);
 		if (interior) {
-			// two complex outputs (four samples) per thread and iteration, no bounds logic
-			for (int i = p.Lh + 2 * tid; i < kM; i += 2 * kConvThreads) {
-				const float4 cc = *reinterpret_cast<const float4*> (sm + phys (i)); // w[i], w[i+1]
-				const float2 cm = sm[phys (i - 1)];
-				const float2 za = ld (i - dl), zb = ld (i + 1 - dl);
-				rawmax = fmaxf (fmaxf (rawmax, fmaxf (fabsf (za.x), fabsf (za.y))), fmaxf (fabsf (zb.x), fabsf (zb.y)));
-				const float r0 = fmaf (za.x, za.x, cm.y * cm.y);
-				const float r1 = fmaf (za.y, za.y, cc.x * cc.x);
-				const float r2 = fmaf (zb.x, zb.x, cc.y * cc.y);
-				const float r3 = fmaf (zb.y, zb.y, cc.z * cc.z);
-				const bool  any = !(fmaxf (fmaxf (r0, r1), fmaxf (r2, r3)) < thr2);
-				if (__any_sync (0xffffffffu, any)) {
-					append_points (lst, cnt, r0 >= thr2, make_float2 (za.x, cm.y), r1 >= thr2, make_float2 (za.y, cc.x), lt, lane);
-					append_points (lst, cnt, r2 >= thr2, make_float2 (zb.x, cc.y), r3 >= thr2, make_float2 (zb.y, cc.z), lt, lane);
+			const int dk = dl >> 9;
+#pragma unroll
+			for (int kb = 8; kb < 32; kb += 4) { // Lh >= 4096
+				if (512 * kb < p.Lh) continue;
+				float2 zd[4];
+				tmem_ld4 (tb + 2 * (kb - dk), zd);
+#pragma unroll
+				for (int kk = 0; kk < 4; ++kk) {
+					const int k  = kb + kk;
+					float     pv = __shfl_up_sync (0xffffffffu, w[k].y, 1);
+					if (lane == 0) pv = xch[xbase + k];
+					rawmax        = fmaxf (rawmax, fmaxf (fabsf (zd[kk].x), fabsf (zd[kk].y)));
+					const bool k0 = fmaf (zd[kk].x, zd[kk].x, pv * pv) >= thr2;
+					const bool k1 = fmaf (zd[kk].y, zd[kk].y, w[k].x * w[k].x) >= thr2;
+					if (__any_sync (0xffffffffu, k0 || k1)) {
+						append_points (lst, cnt, k0, make_float2 (zd[kk].x, pv), k1, make_float2 (zd[kk].y, w[k].x), lt, lane);
+					}
 				}
 			}
 		} else {
-			// edge segment (stream start / end): per element region checks
-			for (int i0 = p.Lh; i0 < kM; i0 += kConvThreads) {
-				const int i  = i0 + tid;
-				bool      k0 = false, k1 = false;
-				float2    p0 = make_float2 (0.f, 0.f), p1 = p0;
-				if (i < cx.i_hi) {
-					const float2 c1 = sm[phys (i)];
-					const float2 c0 = sm[phys (i - 1)];
-					float2       zd = ld (i - dl);
-					rawmax          = fmaxf (rawmax, fmaxf (fabsf (zd.x), fabsf (zd.y)));
-					if (i >= cx.i_skip) {
-						if (i < cx.i_zero) zd = make_float2 (0.f, 0.f);
-						p0 = make_float2 (zd.x, c0.y);
-						p1 = make_float2 (zd.y, c1.x);
-						k0 = fmaf (p0.x, p0.x, p0.y * p0.y) >= thr2;
-						k1 = fmaf (p1.x, p1.x, p1.y * p1.y) >= thr2;
-					}
+#pragma unroll 1
+			for (int kb = 0; kb < 32; kb += 4) {
+				if (512 * (kb + 4) <= p.Lh) continue; // whole block in the overlap region (uniform)
+				float2 zd[4];
+				bool   ok[4];
+#pragma unroll
+				for (int kk = 0; kk < 4; ++kk) {
+					const int i = tid + 512 * (kb + kk);
+					ok[kk]      = i >= p.Lh && i < cx.i_hi;
 				}
-				append_points (lst, cnt, k0, p0, k1, p1, lt, lane);
+				load_direct (zd, ok, tid, kb, dl, tb, ld);
+#pragma unroll
+				for (int kk = 0; kk < 4; ++kk) {
+					const int k  = kb + kk;
+					const int i  = tid + 512 * k;
+					float     wy = w[0].y, wx = w[0].x;
+#pragma unroll
+					for (int kq = 1; kq < 32; ++kq) { // rare path: select instead of unrolling the block loop
+						if (kq == k) {
+							wy = w[kq].y;
+							wx = w[kq].x;
+						}
+					}
+					float pv = __shfl_up_sync (0xffffffffu, wy, 1);
+					if (lane == 0) pv = xch[xbase + k];
+					if (ok[kk]) rawmax = fmaxf (rawmax, fmaxf (fabsf (zd[kk].x), fabsf (zd[kk].y)));
+					const float2 z  = i < cx.i_zero ? make_float2 (0.f, 0.f) : zd[kk];
+					const float2 p0 = make_float2 (z.x, pv), p1 = make_float2 (z.y, wx);
+					const bool   in = ok[kk] && i >= cx.i_skip;
+					const bool   k0 = in && fmaf (p0.x, p0.x, p0.y * p0.y) >= thr2;
+					const bool   k1 = in && fmaf (p1.x, p1.x, p1.y * p1.y) >= thr2;
+					if (__any_sync (0xffffffffu, k0 || k1)) append_points (lst, cnt, k0, p0, k1, p1, lt, lane);
+				}
 			}
 		}
 		cx.rawmax = rawmax;
@@ -419,33 +277,83 @@ __device__ __forceinline__ void epilogue (float2* sm, const ConvParams& p, int t
 		float2*      outc = p.out + (cx.mbase + (long long)cx.c * p.out_stride);
 		const float2 cs   = (EPI == EPI_RENDER) ? p.cs[cx.c] : make_float2 (0.f, 1.f);
 		const int    rlen = (EPI == EPI_RENDER && p.ramp_len) ? p.ramp_len[cx.c] : 0;
-		for (int i = p.Lh + tid; i < cx.i_hi; i += kConvThreads) {
-			const float2 c1 = sm[phys (i)];
-			const float2 c0 = sm[phys (i - 1)];
-			float2       y  = make_float2 (c0.y, c1.x);
-			if (EPI == EPI_RENDER) {
-				const float2    zd  = ld (i - dl);
-				float2          cs0 = cs, cs1 = cs;
-				const long long t0  = 2 * (cx.mbase + i);
-				if (t0 < rlen) {
-					const float2* r = p.ramp + (long long)cx.c * p.ramp_stride + t0;
-					cs0             = r[0];
-					if (t0 + 1 < rlen) cs1 = r[1];
-				}
-				// mul, mul, add like the reference (cli:223, src:700,715)
-				y.x = __fadd_rn (__fmul_rn (cs0.x, zd.x), __fmul_rn (cs0.y, c0.y));
-				y.y = __fadd_rn (__fmul_rn (cs1.x, zd.y), __fmul_rn (cs1.y, c1.x));
+#pragma unroll
+		for (int kb = 0; kb < 32; kb += 4) {
+			if (512 * (kb + 4) <= p.Lh) continue; // whole block in the overlap region (uniform)
+			float2 zd[4];
+			bool   ok[4];
+#pragma unroll
+			for (int kk = 0; kk < 4; ++kk) {
+				const int i = tid + 512 * (kb + kk);
+				ok[kk]      = i >= p.Lh && i < cx.i_hi;
+				zd[kk]      = make_float2 (0.f, 0.f);
 			}
-			__stcs (outc + i, y);
+			if (EPI == EPI_RENDER) load_direct (zd, ok, tid, kb, dl, tb, ld);
+#pragma unroll
+			for (int kk = 0; kk < 4; ++kk) {
+				const int k  = kb + kk;
+				const int i  = tid + 512 * k;
+				float     pv = __shfl_up_sync (0xffffffffu, w[k].y, 1);
+				if (lane == 0) pv = xch[xbase + k];
+				if (ok[kk]) {
+					float2 y = make_float2 (pv, w[k].x);
+					if (EPI == EPI_RENDER) {
+						float2          cs0 = cs, cs1 = cs;
+						const long long t0  = 2 * (cx.mbase + i);
+						if (t0 < rlen) {
+							const float2* r = p.ramp + (long long)cx.c * p.ramp_stride + t0;
+							cs0             = r[0];
+							if (t0 + 1 < rlen) cs1 = r[1];
+						}
+						// mul, mul, add like the reference (cli:223, src:700,715)
+						y.x = __fadd_rn (__fmul_rn (cs0.x, zd[kk].x), __fmul_rn (cs0.y, pv));
+						y.y = __fadd_rn (__fmul_rn (cs1.x, zd[kk].y), __fmul_rn (cs1.y, w[k].x));
+					}
+					__stcs (outc + i, y);
+				}
+			}
 		}
 	}
 }
 
-template <int EPI, class Loader>
-__device__ __forceinline__ void run_segment (float2* sm, const ConvParams& p, int tid, int lane, EpiCtx& cx, const Loader ld)
+// The thread index, re-read from shared memory (volatile) at the start of every
+// pass.  Neither nvcc nor ptxas can see through it, so everything a pass derives
+// from the thread index (addresses, twiddle and filter loads) is recomputed
+// inside the pass instead of being hoisted out of the persistent loop and kept
+// alive - i.e. spilled to local memory - across the other passes, each of which
+// needs the whole register file.
+__device__ __forceinline__ int opaque_tid (const int* tidbuf, int tid)
 {
-	transform_segment (sm, p, tid, ld);
-	epilogue<EPI> (sm, p, tid, lane, cx, ld);
+	return *reinterpret_cast<const volatile int*> (tidbuf + tid);
+}
+
+// One segment: five passes, four shared-memory round trips, epilogue from registers.
+template <int EPI, class Loader>
+__device__ __forceinline__ void run_segment (float2* sm, float* xch, uint32_t tb, const ConvParams& p, int tid, int lane, EpiCtx& cx, const Loader ld)
+{
+	const int* tidbuf = reinterpret_cast<const int*> (xch + kXchFloats + 4);
+	if (EPI != EPI_HILBERT && stash_usable (p.Lh >> 1)) {
+		p1_forward (sm, p.tw1, opaque_tid (tidbuf, tid), ld, TmemStash { tb });
+		tmem_wait_st ();
+	} else {
+		p1_forward (sm, p.tw1, opaque_tid (tidbuf, tid), ld);
+	}
+	__syncthreads ();
+	p2_pass<-1> (sm, opaque_tid (tidbuf, tid));
+	__syncthreads ();
+	mid_pass (sm, reinterpret_cast<const float4*> (p.G), p.tw2, opaque_tid (tidbuf, tid));
+	__syncthreads ();
+	p2_pass<+1> (sm, opaque_tid (tidbuf, tid));
+	__syncthreads ();
+	float2 w[32];
+	p1_inverse (sm, p.tw1, opaque_tid (tidbuf, tid), w);
+	if (lane == 31) {
+		float* x = xch + (tid >> 5) * 32;
+#pragma unroll
+		for (int k = 0; k < 32; ++k) x[k] = w[k].y;
+	}
+	__syncthreads (); // xch visible; every warp is done reading sm, the next segment may overwrite it
+	epilogue<EPI> (w, xch, tb, p, tid, lane, cx, ld);
 }
 
 // ---------------------------------------------------------------------------
@@ -458,7 +366,11 @@ template <int EPI, int SRC>
 __global__ void __launch_bounds__ (kConvThreads, 1) fftconv_kernel (const ConvParams p)
 {
 	extern __shared__ __align__ (16) float2 sm[];
+	float*    xch  = reinterpret_cast<float*> (sm + kM);
 	const int tid  = threadIdx.x;
+	reinterpret_cast<int*> (xch + kXchFloats + 4)[tid] = tid; // see opaque_tid(); made visible by the barrier in tmem_alloc_all()
+	const uint32_t tmem = tmem_alloc_all (reinterpret_cast<uint32_t*> (xch + kXchFloats), tid);
+	const uint32_t tb   = tmem_thread_base (tmem, tid);
 	const int lane = tid & 31;
 
 	EpiCtx cx;
@@ -516,20 +428,19 @@ __global__ void __launch_bounds__ (kConvThreads, 1) fftconv_kernel (const ConvPa
 		}
 
 		if (SRC == SRC_PLANE) {
-			run_segment<EPI> (sm, p, tid, lane, cx, PlaneLoader { p.plane + (long long)c * p.plane_stride + p.padf + n0 });
+			run_segment<EPI> (sm, xch, tb, p, tid, lane, cx, PlaneLoader { p.plane + (long long)c * p.plane_stride + p.padf + n0 });
 		} else {
 			const bool inside = n0 >= 0 && 2 * (n0 + kM) <= p.n_frames;
 			if (!inside) {
-				run_segment<EPI> (sm, p, tid, lane, cx, EdgeLoader { p.inter, p.hist, p.n_frames, 2 * n0, p.C, c, 2 * p.Lh });
+				run_segment<EPI> (sm, xch, tb, p, tid, lane, cx, EdgeLoader { p.inter, p.hist, p.n_frames, 2 * n0, p.C, c, 2 * p.Lh });
 			} else if (p.C == 2 && (reinterpret_cast<uintptr_t> (p.inter) & 15) == 0) {
-				run_segment<EPI> (sm, p, tid, lane, cx, Inter2Loader { reinterpret_cast<const float4*> (p.inter) + n0, c });
+				run_segment<EPI> (sm, xch, tb, p, tid, lane, cx, Inter2Loader { reinterpret_cast<const float4*> (p.inter) + n0, c });
 			} else if (p.C == 1 && (reinterpret_cast<uintptr_t> (p.inter) & 7) == 0) {
-				run_segment<EPI> (sm, p, tid, lane, cx, Inter1Loader { reinterpret_cast<const float2*> (p.inter) + n0 });
+				run_segment<EPI> (sm, xch, tb, p, tid, lane, cx, Inter1Loader { reinterpret_cast<const float2*> (p.inter) + n0 });
 			} else {
-				run_segment<EPI> (sm, p, tid, lane, cx, InterNLoader { p.inter + 2 * n0 * p.C + c, p.C });
+				run_segment<EPI> (sm, xch, tb, p, tid, lane, cx, InterNLoader { p.inter + 2 * n0 * p.C + c, p.C });
 			}
 		}
-		__syncthreads (); // smem is overwritten by the next segment's first pass
 	}
 
 	if (EPI == EPI_POINTS && raw_chan >= 0) {
@@ -537,6 +448,7 @@ __global__ void __launch_bounds__ (kConvThreads, 1) fftconv_kernel (const ConvPa
 		for (int o = 16; o; o >>= 1) r = fmaxf (r, __shfl_xor_sync (0xffffffffu, r, o));
 		if (lane == 0) atomicMax (p.rawpeak + raw_chan, __float_as_uint (r));
 	}
+	tmem_free_all (tmem, tid);
 }
 
 // ---------------------------------------------------------------------------

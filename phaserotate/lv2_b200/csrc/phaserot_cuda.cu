@@ -9,6 +9,7 @@
 // launch, and create() refuses to hand out a handle without an sm_100 device.
 #include "../../../include/phaserot_cuda.h"
 #include "kernels.cuh"
+#include "fft16k_tables.h"
 
 #include <algorithm>
 #include <cmath>
@@ -68,38 +69,6 @@ design_fir (int L, bool plugin, std::vector<float>& taps)
 		const float  raw = (float)(-2.0 / std::tan (M_PI * (double)m / (double)L));
 		const double win = scale * (1.0 - std::cos (2.0 * M_PI * (double)i * (1.0 / (double)L)));
 		taps[(size_t)i]  = (float)((double)raw * win);
-	}
-}
-
-// in-place radix-2 complex FFT (double), n a power of two; sign -1 forward
-void
-host_fft (std::vector<double>& re, std::vector<double>& im, int sign)
-{
-	const size_t n = re.size ();
-	for (size_t i = 1, j = 0; i < n; ++i) {
-		size_t bit = n >> 1;
-		for (; j & bit; bit >>= 1) {
-			j ^= bit;
-		}
-		j ^= bit;
-		if (i < j) {
-			std::swap (re[i], re[j]);
-			std::swap (im[i], im[j]);
-		}
-	}
-	for (size_t len = 2; len <= n; len <<= 1) {
-		const double ang = sign * 2.0 * M_PI / (double)len;
-		for (size_t i = 0; i < n; i += len) {
-			for (size_t k = 0; k < len / 2; ++k) {
-				const double wr = std::cos (ang * (double)k), wi = std::sin (ang * (double)k);
-				const size_t a = i + k, b = i + k + len / 2;
-				const double tr = re[b] * wr - im[b] * wi, ti = re[b] * wi + im[b] * wr;
-				re[b] = re[a] - tr;
-				im[b] = im[a] - ti;
-				re[a] += tr;
-				im[a] += ti;
-			}
-		}
 	}
 }
 
@@ -336,44 +305,23 @@ unsigned long long* d_stats (phaserot* h) { return (unsigned long long*)((char*)
 int
 upload_tables (phaserot* h)
 {
-	// filter spectrum in the order the forward passes leave it in, scaled by 1/M
+	// odd taps g[j] = fir[2j + 1]: the complex half-rate convolution kernel
 	const int Lh = h->Lh;
-	std::vector<double> re ((size_t)kM, 0.0), im ((size_t)kM, 0.0);
+	std::vector<float> g ((size_t)Lh);
 	for (int j = 0; j < Lh; ++j) {
-		re[(size_t)j] = (double)h->taps[(size_t)(2 * j + 1)];
+		g[(size_t)j] = h->taps[(size_t)(2 * j + 1)];
 	}
-	host_fft (re, im, -1);
-	std::vector<float2> G ((size_t)kM);
-	for (int p = 0; p < kM; ++p) {
-		const int q1 = p >> 10, q2 = (p >> 6) & 15, q3 = (p >> 2) & 15, q4 = p & 3;
-		const int f  = q1 + 16 * q2 + 256 * q3 + 4096 * q4;
-		G[(size_t)p] = make_float2 ((float)(re[(size_t)f] / kM), (float)(im[(size_t)f] / kM));
-	}
+	// filter spectrum / M in MID-pass order, twiddles (fft16k_tables.h)
+	const std::vector<float2> G = make_filter_spectrum (g.data (), Lh);
 	int rc = h->d_G.ensure (sizeof (float2) * kM);
 	if (rc) return rc;
 	CK (cudaMemcpy (h->d_G.p, G.data (), sizeof (float2) * kM, cudaMemcpyHostToDevice));
-
-	// twiddles W_n^(j q), q in {1,2,3,4,8,12}: [6][1024] | [6][64] | [6][4]
-	static const int qs[6] = { 1, 2, 3, 4, 8, 12 };
-	std::vector<float2> tw;
-	for (int stride : { 1024, 64, 4 }) {
-		const double n = 16.0 * stride;
-		for (int r = 0; r < 6; ++r) {
-			for (int j = 0; j < stride; ++j) {
-				const double a = -2.0 * M_PI * (double)j * qs[r] / n;
-				tw.push_back (make_float2 ((float)std::cos (a), (float)std::sin (a)));
-			}
-		}
-	}
+	const std::vector<float2> tw = make_twiddles ();
 	rc = h->d_tw.ensure (sizeof (float2) * tw.size ());
 	if (rc) return rc;
 	CK (cudaMemcpy (h->d_tw.p, tw.data (), sizeof (float2) * tw.size (), cudaMemcpyHostToDevice));
 
 	// odd taps for the direct-form small-call path
-	std::vector<float> g ((size_t)Lh);
-	for (int j = 0; j < Lh; ++j) {
-		g[(size_t)j] = h->taps[(size_t)(2 * j + 1)];
-	}
 	rc = h->d_g.ensure (sizeof (float) * (size_t)Lh);
 	if (rc) return rc;
 	CK (cudaMemcpy (h->d_g.p, g.data (), sizeof (float) * (size_t)Lh, cudaMemcpyHostToDevice));
@@ -389,8 +337,7 @@ fill_conv_common (phaserot* h, ConvParams& p)
 	p.padf         = h->padf;
 	p.G            = (const float2*)h->d_G.p;
 	p.tw1          = (const float2*)h->d_tw.p;
-	p.tw2          = p.tw1 + 6 * 1024;
-	p.tw3          = p.tw2 + 6 * 64;
+	p.tw2          = p.tw1 + kTwP1Rows * 512;
 	p.Lh           = h->Lh;
 	p.V            = h->V;
 	p.seg_stride   = 1;
