@@ -57,14 +57,18 @@ PRK_HD float2 caddi (float2 a, float2 b) { return __fadd2_rn (a, make_float2 (-b
 PRK_HD float2 csubi (float2 a, float2 b) { return __fadd2_rn (a, make_float2 (b.y, -b.x)); } // a - i b
 // a * b = b.x * a + b.y * (i a): the factor b enters only through broadcasts of its
 // two components and the data a through a swap / negate modifier, so neither
-// product needs a rearranged copy of b (and a * conj(b) needs no negated one)
+// product needs a rearranged copy of b (and a * conj(b) needs no negated one).
+// Operand order matters: the half-negating modifier (.NP) exists only for the
+// first source operand, the .F32 broadcast for either, and the compiler does not
+// commute the operands (probed with cuobjdump; a swapped order costs an extra
+// FADD + MOV per product).
 PRK_HD float2 cmul (float2 a, float2 b)
 {
-	return __ffma2_rn (make_float2 (b.y, b.y), make_float2 (-a.y, a.x), __fmul2_rn (make_float2 (b.x, b.x), a));
+	return __ffma2_rn (make_float2 (-a.y, a.x), make_float2 (b.y, b.y), __fmul2_rn (a, make_float2 (b.x, b.x)));
 }
 PRK_HD float2 cmulc (float2 a, float2 b) // a * conj(b) = b.x * a - b.y * (i a)
 {
-	return __ffma2_rn (make_float2 (b.y, b.y), make_float2 (a.y, -a.x), __fmul2_rn (make_float2 (b.x, b.x), a));
+	return __ffma2_rn (make_float2 (a.y, -a.x), make_float2 (b.y, b.y), __fmul2_rn (a, make_float2 (b.x, b.x)));
 }
 #else
 PRK_HD float2 cadd (float2 a, float2 b) { return make_float2 (a.x + b.x, a.y + b.y); }
@@ -402,8 +406,14 @@ PRK_HD void mid_pass (float2* sm, const float4* __restrict__ G4, const float2* _
 		dft16<+1> (u);
 #pragma unroll
 		for (int j = 1; j < 16; ++j) u[j] = cmulc (u[j], tw[j]);
+		// two 8-byte stores per chunk: a 16-byte store would need both results in
+		// one aligned register quad, which costs moves
+		float2* rp2 = reinterpret_cast<float2*> (rp);
 #pragma unroll
-		for (int c = 0; c < 8; ++c) rp[c ^ s] = make_float4 (u[2 * c].x, u[2 * c].y, u[2 * c + 1].x, u[2 * c + 1].y);
+		for (int c = 0; c < 8; ++c) {
+			rp2[2 * (c ^ s)]     = u[2 * c];
+			rp2[2 * (c ^ s) + 1] = u[2 * c + 1];
+		}
 	}
 }
 

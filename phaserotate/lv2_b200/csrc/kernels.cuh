@@ -223,16 +223,22 @@ __device__ __forceinline__ void epilogue (const float2 (&w)[32], const float* xc
 				if (512 * kb < p.Lh) continue;
 				float2 zd[4];
 				tmem_ld4 (tb + 2 * (kb - dk), zd);
+				float pv[4];
+				bool  k0[4], k1[4], any = false;
 #pragma unroll
 				for (int kk = 0; kk < 4; ++kk) {
-					const int k  = kb + kk;
-					float     pv = __shfl_up_sync (0xffffffffu, w[k].y, 1);
-					if (lane == 0) pv = xch[xbase + k];
-					rawmax        = fmaxf (rawmax, fmaxf (fabsf (zd[kk].x), fabsf (zd[kk].y)));
-					const bool k0 = fmaf (zd[kk].x, zd[kk].x, pv * pv) >= thr2;
-					const bool k1 = fmaf (zd[kk].y, zd[kk].y, w[k].x * w[k].x) >= thr2;
-					if (__any_sync (0xffffffffu, k0 || k1)) {
-						append_points (lst, cnt, k0, make_float2 (zd[kk].x, pv), k1, make_float2 (zd[kk].y, w[k].x), lt, lane);
+					const int k = kb + kk;
+					pv[kk]      = __shfl_up_sync (0xffffffffu, w[k].y, 1);
+					if (lane == 0) pv[kk] = xch[xbase + k];
+					rawmax = fmaxf (rawmax, fmaxf (fabsf (zd[kk].x), fabsf (zd[kk].y)));
+					k0[kk] = fmaf (zd[kk].x, zd[kk].x, pv[kk] * pv[kk]) >= thr2;
+					k1[kk] = fmaf (zd[kk].y, zd[kk].y, w[k].x * w[k].x) >= thr2;
+					any    = any || k0[kk] || k1[kk];
+				}
+				if (__any_sync (0xffffffffu, any)) { // one vote per eight samples; survivors are a fraction of a percent
+#pragma unroll
+					for (int kk = 0; kk < 4; ++kk) {
+						append_points (lst, cnt, k0[kk], make_float2 (zd[kk].x, pv[kk]), k1[kk], make_float2 (zd[kk].y, w[kb + kk].x), lt, lane);
 					}
 				}
 			}
@@ -377,10 +383,10 @@ __global__ void __launch_bounds__ (kConvThreads, 1) fftconv_kernel (const ConvPa
 	cx.rawmax    = 0.f;
 	int raw_chan = -1;
 
-	const long long total = p.nseg * p.nchan;
-	for (long long w = blockIdx.x; w < total; w += gridDim.x) {
-		const long long si  = w / p.nchan;
-		const int       ci  = (int)(w - si * p.nchan);
+	const int total = (int)(p.nseg * p.nchan); // a launch covers at most a few thousand work items
+	for (int w = blockIdx.x; w < total; w += gridDim.x) {
+		const int       si  = w / p.nchan;
+		const int       ci  = w - si * p.nchan;
 		const long long seg = p.seg0 + si * p.seg_stride;
 		const int       c   = p.chan0 + ci;
 		const long long n0  = seg * p.V - p.Lh; // complex stream index of local index 0
@@ -397,10 +403,10 @@ __global__ void __launch_bounds__ (kConvThreads, 1) fftconv_kernel (const ConvPa
 		}
 		{
 			// pull this CTA's next segment towards L2 while this one is transformed
-			const long long wn = w + gridDim.x;
+			const int wn = w + gridDim.x;
 			if (wn < total) {
-				const long long sn  = wn / p.nchan;
-				const int       cn  = (int)(wn - sn * p.nchan);
+				const int sn = wn / p.nchan;
+				const int cn = wn - sn * p.nchan;
 				const long long nn0 = (p.seg0 + sn * p.seg_stride) * p.V - p.Lh;
 				const char*     pf;
 				long long       nbytes;

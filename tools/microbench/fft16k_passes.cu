@@ -13,6 +13,9 @@ using namespace prk;
 #ifndef STAGGER
 #define STAGGER 0
 #endif
+#ifndef DELAY_NS
+#define DELAY_NS 250
+#endif
 
 template <int WHICH>
 __global__ void __launch_bounds__ (512, 1) pass_kernel (const float4* src4, const float2* src2, const float2* tw, const float4* G, float2* out, int iters, long long* cyc)
@@ -28,6 +31,18 @@ __global__ void __launch_bounds__ (512, 1) pass_kernel (const float4* src4, cons
 		if (WHICH == 1) p1_forward (sm, tw, tid, Inter2Loader { src4 + (size_t)(blockIdx.x * 7 + it) % 64 * kM, it & 1 });
 		if (WHICH == 2) p2_pass<-1> (sm, tid);
 		if (WHICH == 3) mid_pass (sm, G, tw + kTwP1Rows * 512, tid);
+		if (WHICH == 8) { // MID, upper half of the warps delayed
+			if (tid >= 256) __nanosleep (DELAY_NS);
+			mid_pass (sm, G, tw + kTwP1Rows * 512, tid);
+		}
+		if (WHICH == 9) { // P2, upper half of the warps delayed
+			if (tid >= 256) __nanosleep (DELAY_NS);
+			p2_pass<-1> (sm, tid);
+		}
+		if (WHICH == 10) { // MID, quarter offsets
+			if (tid >= 128) __nanosleep (DELAY_NS / 2 * (tid >> 7));
+			mid_pass (sm, G, tw + kTwP1Rows * 512, tid);
+		}
 		if (WHICH == 4) {
 			float2 w[32];
 			p1_inverse (sm, tw, tid, w);
@@ -115,5 +130,9 @@ int main ()
 	run<5> ("dft32 only (+64 packed adds)", src4, dtw, (const float4*)dG, out, cyc);
 	run<6> ("P2 smem traffic only", src4, dtw, (const float4*)dG, out, cyc);
 	run<7> ("MID arithmetic only (2 rows)", src4, dtw, (const float4*)dG, out, cyc);
+	printf ("DELAY_NS=%d\n", DELAY_NS);
+	run<8> ("MID, half the warps delayed", src4, dtw, (const float4*)dG, out, cyc);
+	run<9> ("P2, half the warps delayed", src4, dtw, (const float4*)dG, out, cyc);
+	run<10> ("MID, quarter offsets", src4, dtw, (const float4*)dG, out, cyc);
 	return 0;
 }
