@@ -346,11 +346,17 @@ PRK_HD void p1_forward (float2* sm, const float2* __restrict__ tw, int e, const 
 	}
 }
 
-// P2: radix-32 over i1 (forward) / q2 (inverse) for fixed (q1, i0).  Thread t = q1 * 16 + i0.
+// P2: radix-32 over i1 (forward) / q2 (inverse) for fixed (q1, i0).  Warp wp
+// handles the two 512-point blocks q1 = wp (lanes 0..15, i0 = lane) and
+// q1 = wp + 16 (lanes 16..31) - the same two blocks whose rows it owns in MID
+// (rows t and t + 512), so P2 -> MID -> P2' of a block pair runs inside one warp
+// with warp-level synchronisation only and the warps drift apart: while one
+// waits for shared memory another one has the FMA pipe.
+PRK_HD int p2_block (int t) { return (t >> 5) + 16 * ((t >> 4) & 1); }
 template <int DIR>
 PRK_HD void p2_pass (float2* sm, int t)
 {
-	const SwzCol so = swz_col ((t >> 4) * 32, t & 15); // row = 32 q1 + k: key term k & 7
+	const SwzCol so = swz_col (p2_block (t) * 32, t & 15); // row = 32 q1 + k: key term k & 7
 	float2       s1[8][4];
 	{
 		float2 u[8][4];

@@ -345,10 +345,11 @@ __device__ __forceinline__ void run_segment (float2* sm, float* xch, uint32_t tb
 		p1_forward (sm, p.tw1, opaque_tid (tidbuf, tid), ld);
 	}
 	__syncthreads ();
+	// the three middle passes of a block pair stay inside one warp (see p2_block())
 	p2_pass<-1> (sm, opaque_tid (tidbuf, tid));
-	__syncthreads ();
+	__syncwarp ();
 	mid_pass (sm, reinterpret_cast<const float4*> (p.G), p.tw2, opaque_tid (tidbuf, tid));
-	__syncthreads ();
+	__syncwarp ();
 	p2_pass<+1> (sm, opaque_tid (tidbuf, tid));
 	__syncthreads ();
 	float2 w[32];
