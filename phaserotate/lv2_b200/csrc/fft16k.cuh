@@ -378,9 +378,24 @@ PRK_HD void p2_pass (float2* sm, int t)
 }
 
 // MID: rows t and t + 512 (same q2 = t & 31): twiddle, radix-16, filter, inverse
-// radix-16, conjugate twiddle.  G4[c * 1024 + row] = (G[f(row, 2c)], G[f(row, 2c + 1)]),
-// f(row, q3) = (row >> 5) + 32 (row & 31) + 1024 q3, already scaled by 1 / M.
-PRK_HD void mid_pass (float2* sm, const float4* __restrict__ G4, const float2* __restrict__ twm, int t)
+// radix-16, conjugate twiddle.  The filter spectrum of a row, already scaled by
+// 1 / M, comes from `gs`:  gs.issue (h) starts fetching the 16 bins
+// G[f(row, q3)], f(row, q3) = (row >> 5) + 32 (row & 31) + 1024 q3, of row
+// t + 512 h and gs.get (g) delivers them as g[c] = (G[f(row, 2c)], G[f(row, 2c + 1)]).
+// On the device that is the thread's Tensor Memory stash (kernels.cuh), in the
+// host emulation and the microbenchmarks the table itself.
+struct GTable { // G4[c * 1024 + row] as built by make_filter_spectrum()
+	const float4* G4;
+	int           t, row;
+	PRK_HD void issue (int h) { row = t + 512 * h; }
+	PRK_HD void get (float4 (&g)[8]) const
+	{
+#pragma unroll
+		for (int c = 0; c < 8; ++c) g[c] = PRK_LDG (G4 + c * 1024 + row);
+	}
+};
+template <class GSrc>
+PRK_HD void mid_pass (float2* sm, GSrc gs, const float2* __restrict__ twm, int t)
 {
 	const int q2 = t & 31;
 	float2    tw[16];
@@ -391,9 +406,7 @@ PRK_HD void mid_pass (float2* sm, const float4* __restrict__ G4, const float2* _
 		const int row = t + 512 * h;
 		const int s   = ((row >> 5) ^ row) & 7;
 		float4*   rp  = reinterpret_cast<float4*> (sm + (row << 4));
-		float4    g[8];
-#pragma unroll
-		for (int c = 0; c < 8; ++c) g[c] = PRK_LDG (G4 + c * 1024 + row);
+		gs.issue (h);
 		float2 u[16];
 #pragma unroll
 		for (int c = 0; c < 8; ++c) {
@@ -404,6 +417,8 @@ PRK_HD void mid_pass (float2* sm, const float4* __restrict__ G4, const float2* _
 #pragma unroll
 		for (int j = 1; j < 16; ++j) u[j] = cmul (u[j], tw[j]);
 		dft16<-1> (u);
+		float4 g[8];
+		gs.get (g);
 #pragma unroll
 		for (int c = 0; c < 8; ++c) {
 			u[2 * c]     = cmul (u[2 * c], make_float2 (g[c].x, g[c].y));

@@ -181,6 +181,22 @@ struct TmemStash {
 	__device__ __forceinline__ void operator() (int k, float2 a, float2 b, float2 c, float2 d) const { tmem_st4 (tb + 2 * k, a, b, c, d); }
 };
 
+// Filter spectrum of the thread's two MID rows, parked in TMEM columns
+// kTmemGCol .. kTmemGCol + 63 by fftconv_kernel before the first segment.
+struct GTmem {
+	uint32_t tb;
+	uint32_t r[32];
+	__device__ __forceinline__ void issue (int h) { tmem_ld16_issue (tb + kTmemGCol + 32 * h, r); }
+	__device__ __forceinline__ void get (float4 (&g)[8])
+	{
+		tmem_wait_ld16 (r);
+#pragma unroll
+		for (int c = 0; c < 8; ++c) {
+			g[c] = make_float4 (__uint_as_float (r[4 * c]), __uint_as_float (r[4 * c + 1]), __uint_as_float (r[4 * c + 2]), __uint_as_float (r[4 * c + 3]));
+		}
+	}
+};
+
 // The stash serves the epilogue when the delay Lh/2 is a multiple of 2048 points:
 // output block kb .. kb + 3 then needs the aligned input block kb - Lh/1024 of
 // the same thread (Lh = 4096 and 8192, i.e. the CLI block sizes 8192 and 16384).
@@ -348,7 +364,7 @@ __device__ __forceinline__ void run_segment (float2* sm, float* xch, uint32_t tb
 	// the three middle passes of a block pair stay inside one warp (see p2_block())
 	p2_pass<-1> (sm, opaque_tid (tidbuf, tid));
 	__syncwarp ();
-	mid_pass (sm, reinterpret_cast<const float4*> (p.G), p.tw2, opaque_tid (tidbuf, tid));
+	mid_pass (sm, GTmem { tb }, p.tw2, opaque_tid (tidbuf, tid));
 	__syncwarp ();
 	p2_pass<+1> (sm, opaque_tid (tidbuf, tid));
 	__syncthreads ();
@@ -379,18 +395,39 @@ __global__ void __launch_bounds__ (kConvThreads, 1) fftconv_kernel (const ConvPa
 	const uint32_t tmem = tmem_alloc_all (reinterpret_cast<uint32_t*> (xch + kXchFloats), tid);
 	const uint32_t tb   = tmem_thread_base (tmem, tid);
 	const int lane = tid & 31;
+	{
+		// this thread's share of the filter spectrum -> TMEM (rows tid and tid + 512 of MID)
+		const float4* G4 = reinterpret_cast<const float4*> (p.G);
+#pragma unroll
+		for (int h = 0; h < 2; ++h) {
+#pragma unroll
+			for (int c = 0; c < 8; c += 2) {
+				const float4 a = __ldg (G4 + c * 1024 + tid + 512 * h), b = __ldg (G4 + (c + 1) * 1024 + tid + 512 * h);
+				tmem_st4 (tb + kTmemGCol + 32 * h + 4 * c, make_float2 (a.x, a.y), make_float2 (a.z, a.w), make_float2 (b.x, b.y), make_float2 (b.z, b.w));
+			}
+		}
+		tmem_wait_st ();
+	}
 
 	EpiCtx cx;
 	cx.rawmax    = 0.f;
 	int raw_chan = -1;
 
+	// work item w = si * nchan + ci (channel fastest); (si, ci) advance without a division
 	const int total = (int)(p.nseg * p.nchan); // a launch covers at most a few thousand work items
+	const int gq = (int)gridDim.x / p.nchan, gr = (int)gridDim.x - gq * p.nchan;
+	int       si = (int)blockIdx.x / p.nchan, ci = (int)blockIdx.x - si * p.nchan;
 	for (int w = blockIdx.x; w < total; w += gridDim.x) {
-		const int       si  = w / p.nchan;
-		const int       ci  = w - si * p.nchan;
 		const long long seg = p.seg0 + si * p.seg_stride;
 		const int       c   = p.chan0 + ci;
 		const long long n0  = seg * p.V - p.Lh; // complex stream index of local index 0
+		int sn = si + gq, cn = ci + gr; // this CTA's next work item
+		if (cn >= p.nchan) {
+			cn -= p.nchan;
+			++sn;
+		}
+		si = sn;
+		ci = cn;
 
 		if (EPI == EPI_POINTS && c != raw_chan) {
 			if (raw_chan >= 0) {
@@ -402,25 +439,23 @@ __global__ void __launch_bounds__ (kConvThreads, 1) fftconv_kernel (const ConvPa
 			raw_chan  = c;
 			cx.rawmax = 0.f;
 		}
-		{
-			// pull this CTA's next segment towards L2 while this one is transformed
-			const int wn = w + gridDim.x;
-			if (wn < total) {
-				const int sn = wn / p.nchan;
-				const int cn = wn - sn * p.nchan;
-				const long long nn0 = (p.seg0 + sn * p.seg_stride) * p.V - p.Lh;
-				const char*     pf;
-				long long       nbytes;
-				if (SRC == SRC_PLANE) {
-					pf     = reinterpret_cast<const char*> (p.plane + (long long)(p.chan0 + cn) * p.plane_stride + p.padf + nn0);
-					nbytes = (long long)kM * (long long)sizeof (float2);
-				} else {
-					pf     = reinterpret_cast<const char*> (p.inter + 2 * nn0 * p.C);
-					nbytes = (cn == 0 && nn0 >= 0 && 2 * (nn0 + kM) <= p.n_frames) ? (long long)kM * 2 * p.C * (long long)sizeof (float) : 0;
-				}
-				for (long long l = (long long)tid * 128; l < nbytes; l += (long long)kConvThreads * 128) {
-					asm volatile ("prefetch.global.L2 [%0];" ::"l"(pf + l));
-				}
+		if (w + (int)gridDim.x < total && lane == 0) {
+			// pull the next segment towards L2 while this one is transformed: one
+			// bulk prefetch per warp, 16 pieces
+			const long long nn0 = (p.seg0 + sn * p.seg_stride) * p.V - p.Lh;
+			const char*     pf;
+			long long       nbytes;
+			if (SRC == SRC_PLANE) {
+				pf     = reinterpret_cast<const char*> (p.plane + (long long)(p.chan0 + cn) * p.plane_stride + p.padf + nn0);
+				nbytes = (long long)kM * (long long)sizeof (float2);
+			} else {
+				pf     = reinterpret_cast<const char*> (p.inter + 2 * nn0 * p.C);
+				nbytes = (cn == 0 && nn0 >= 0 && 2 * (nn0 + kM) <= p.n_frames) ? (long long)kM * 2 * p.C * (long long)sizeof (float) : 0;
+			}
+			if (nbytes > 0) {
+				const unsigned piece = (unsigned)(nbytes >> 4) & ~15u;
+				const char*    a     = reinterpret_cast<const char*> (reinterpret_cast<uintptr_t> (pf) & ~(uintptr_t)15) + (size_t)(tid >> 5) * piece;
+				asm volatile ("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(piece) : "memory");
 			}
 		}
 

@@ -8,7 +8,10 @@
 // a kernel without tensor-core work) is laid out as 128 lanes x 512 columns of
 // 32 bits; with the 32x32b access shape lane l of warp w owns TMEM lane
 // 32 (w % 4) + l, so it is exactly a per-thread scratch.  The four warps that
-// share a lane quarter take 64 columns each: 32 complex inputs per thread.
+// share a lane quarter take 128 columns each: columns 0..63 hold the thread's 32
+// complex inputs, columns 64..127 the filter spectrum of the two MID rows the
+// thread owns (constant for the whole launch; loaded once instead of streaming
+// 128 KB per segment through L1).
 #pragma once
 
 #include <cuda_runtime.h>
@@ -16,7 +19,8 @@
 
 namespace prk {
 
-constexpr int kTmemCols = 256;
+constexpr int kTmemCols = 512;
+constexpr int kTmemGCol = 64; // first column of the filter spectrum
 
 // warp 0 allocates; the base address lands in *slot (shared memory); call with all threads
 __device__ __forceinline__ uint32_t tmem_alloc_all (uint32_t* slot, int tid)
@@ -43,7 +47,7 @@ __device__ __forceinline__ void tmem_free_all (uint32_t base, int tid)
 __device__ __forceinline__ uint32_t tmem_thread_base (uint32_t base, int tid)
 {
 	const int warp = tid >> 5;
-	return base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 64);
+	return base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * 128);
 }
 // four complex values <-> eight consecutive columns
 __device__ __forceinline__ void tmem_st4 (uint32_t taddr, float2 a, float2 b, float2 c, float2 d)
@@ -66,6 +70,31 @@ __device__ __forceinline__ void tmem_ld4 (uint32_t taddr, float2 (&v)[4])
 	v[1] = make_float2 (__uint_as_float (r2), __uint_as_float (r3));
 	v[2] = make_float2 (__uint_as_float (r4), __uint_as_float (r5));
 	v[3] = make_float2 (__uint_as_float (r6), __uint_as_float (r7));
+}
+
+// sixteen complex values = 32 consecutive columns; tmem_wait_ld16() makes them usable
+__device__ __forceinline__ void tmem_ld16_issue (uint32_t taddr, uint32_t (&r)[32])
+{
+	asm volatile ("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+	              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+	              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+	              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+	                "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+	                "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+	                "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+	              : "r"(taddr)
+	              : "memory");
+}
+// the registers pass through the wait so that no use can be scheduled before it
+__device__ __forceinline__ void tmem_wait_ld16 (uint32_t (&r)[32])
+{
+	asm volatile ("tcgen05.wait::ld.sync.aligned;"
+	              : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+	                "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
+	                "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
+	                "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+	              :
+	              : "memory");
 }
 
 } // namespace prk

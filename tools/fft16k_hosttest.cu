@@ -73,7 +73,7 @@ main (int argc, char** argv)
 	std::vector<float2> sm ((size_t)kM);
 	for (int e = 0; e < kConvThreads; ++e) p1_forward (sm.data (), twp1, e, VecLoader { z.data () });
 	for (int t = 0; t < kConvThreads; ++t) p2_pass<-1> (sm.data (), t);
-	for (int t = 0; t < kConvThreads; ++t) mid_pass (sm.data (), reinterpret_cast<const float4*> (G.data ()), twm, t);
+	for (int t = 0; t < kConvThreads; ++t) mid_pass (sm.data (), GTable { reinterpret_cast<const float4*> (G.data ()), t, 0 }, twm, t);
 	for (int t = 0; t < kConvThreads; ++t) p2_pass<+1> (sm.data (), t);
 	std::vector<float2> out ((size_t)kM);
 	for (int e = 0; e < kConvThreads; ++e) {

@@ -30,10 +30,10 @@ __global__ void __launch_bounds__ (512, 1) pass_kernel (const float4* src4, cons
 		if (WHICH == 0) p1_forward (sm, tw, tid, Inter1Loader { src2 + (size_t)(blockIdx.x * 7 + it) % 64 * kM });
 		if (WHICH == 1) p1_forward (sm, tw, tid, Inter2Loader { src4 + (size_t)(blockIdx.x * 7 + it) % 64 * kM, it & 1 });
 		if (WHICH == 2) p2_pass<-1> (sm, tid);
-		if (WHICH == 3) mid_pass (sm, G, tw + kTwP1Rows * 512, tid);
+		if (WHICH == 3) mid_pass (sm, GTable { G, tid, 0 }, tw + kTwP1Rows * 512, tid);
 		if (WHICH == 8) { // MID, upper half of the warps delayed
 			if (tid >= 256) __nanosleep (DELAY_NS);
-			mid_pass (sm, G, tw + kTwP1Rows * 512, tid);
+			mid_pass (sm, GTable { G, tid, 0 }, tw + kTwP1Rows * 512, tid);
 		}
 		if (WHICH == 9) { // P2, upper half of the warps delayed
 			if (tid >= 256) __nanosleep (DELAY_NS);
@@ -41,7 +41,7 @@ __global__ void __launch_bounds__ (512, 1) pass_kernel (const float4* src4, cons
 		}
 		if (WHICH == 10) { // MID, quarter offsets
 			if (tid >= 128) __nanosleep (DELAY_NS / 2 * (tid >> 7));
-			mid_pass (sm, G, tw + kTwP1Rows * 512, tid);
+			mid_pass (sm, GTable { G, tid, 0 }, tw + kTwP1Rows * 512, tid);
 		}
 		if (WHICH == 4) {
 			float2 w[32];
