@@ -313,9 +313,15 @@ PRK_HD float2 apply_tw_p1 (float2 v, const TwP1& t, int ql, int qh)
 struct NoStash {
 	PRK_HD void operator() (int, float2, float2, float2, float2) const {}
 };
+// `reuse (k, v)`: if the raw inputs k .. k + 3 (k a multiple of 4) are already at
+// hand (overlap with the previous segment of the same stream), deliver them and
+// return true
+struct NoReuse {
+	PRK_HD bool operator() (int, float2 (&)[4]) const { return false; }
+};
 // `stash (k, a, b, c, d)` receives the raw inputs k .. k + 3 (k a multiple of 4)
-template <class Loader, class Stash = NoStash>
-PRK_HD void p1_forward (float2* sm, const float2* __restrict__ tw, int e, const Loader& ld, const Stash& stash = Stash ())
+template <class Loader, class Stash = NoStash, class Reuse = NoReuse>
+PRK_HD void p1_forward (float2* sm, const float2* __restrict__ tw, int e, const Loader& ld, const Stash& stash = Stash (), const Reuse& reuse = Reuse ())
 {
 	float2     t[8][4];
 	const auto lt = ld.thread (e);
@@ -323,9 +329,15 @@ PRK_HD void p1_forward (float2* sm, const float2* __restrict__ tw, int e, const 
 	for (int half = 0; half < 2; ++half) {
 		float2 u[4][4];
 #pragma unroll
-		for (int kk = 0; kk < 4; ++kk) {
+		for (int k1 = 0; k1 < 4; ++k1) {
+			float2 v[4];
+			if (reuse (4 * half + 8 * k1, v)) {
 #pragma unroll
-			for (int k1 = 0; k1 < 4; ++k1) u[kk][k1] = lt (512 * (4 * half + kk + 8 * k1));
+				for (int kk = 0; kk < 4; ++kk) u[kk][k1] = v[kk];
+			} else {
+#pragma unroll
+				for (int kk = 0; kk < 4; ++kk) u[kk][k1] = lt (512 * (4 * half + kk + 8 * k1));
+			}
 		}
 #pragma unroll
 		for (int k1 = 0; k1 < 4; ++k1) stash (4 * half + 8 * k1, u[0][k1], u[1][k1], u[2][k1], u[3][k1]);

@@ -197,6 +197,22 @@ struct GTmem {
 	}
 };
 
+// Overlap-save reuse: a CTA walks consecutive segments of one channel, so the
+// first Lh points of a segment are the last Lh of the previous one - still in
+// the TMEM stash (input k of the previous segment sits in columns 2k, 2k + 1).
+// `rows` = Lh / 512 when the previous segment is the stream predecessor, else 0;
+// `shift` = V / 512.
+struct TmemReuse {
+	uint32_t tb;
+	int      rows, shift;
+	__device__ __forceinline__ bool operator() (int k, float2 (&v)[4]) const
+	{
+		if (k >= rows) return false;
+		tmem_ld4 (tb + 2 * (k + shift), v);
+		return true;
+	}
+};
+
 // The stash serves the epilogue when the delay Lh/2 is a multiple of 2048 points:
 // output block kb .. kb + 3 then needs the aligned input block kb - Lh/1024 of
 // the same thread (Lh = 4096 and 8192, i.e. the CLI block sizes 8192 and 16384).
@@ -351,11 +367,11 @@ __device__ __forceinline__ int opaque_tid (const int* tidbuf, int tid)
 
 // One segment: five passes, four shared-memory round trips, epilogue from registers.
 template <int EPI, class Loader>
-__device__ __forceinline__ void run_segment (float2* sm, float* xch, uint32_t tb, const ConvParams& p, int tid, int lane, EpiCtx& cx, const Loader ld)
+__device__ __forceinline__ void run_segment (float2* sm, float* xch, uint32_t tb, const ConvParams& p, int tid, int lane, EpiCtx& cx, const Loader ld, int reuse_rows = 0)
 {
 	const int* tidbuf = reinterpret_cast<const int*> (xch + kXchFloats + 4);
 	if (EPI != EPI_HILBERT && stash_usable (p.Lh >> 1)) {
-		p1_forward (sm, p.tw1, opaque_tid (tidbuf, tid), ld, TmemStash { tb });
+		p1_forward (sm, p.tw1, opaque_tid (tidbuf, tid), ld, TmemStash { tb }, TmemReuse { tb, reuse_rows, p.V >> 9 });
 		tmem_wait_st ();
 	} else {
 		p1_forward (sm, p.tw1, opaque_tid (tidbuf, tid), ld);
@@ -410,47 +426,35 @@ __global__ void __launch_bounds__ (kConvThreads, 1) fftconv_kernel (const ConvPa
 	}
 
 	EpiCtx cx;
-	cx.rawmax    = 0.f;
-	int raw_chan = -1;
+	cx.rawmax = 0.f;
 
-	// work item w = si * nchan + ci (channel fastest); (si, ci) advance without a division
-	const int total = (int)(p.nseg * p.nchan); // a launch covers at most a few thousand work items
-	const int gq = (int)gridDim.x / p.nchan, gr = (int)gridDim.x - gq * p.nchan;
-	int       si = (int)blockIdx.x / p.nchan, ci = (int)blockIdx.x - si * p.nchan;
-	for (int w = blockIdx.x; w < total; w += gridDim.x) {
+	// CTA b owns channel b % nchan and, among the CTAs of that channel, a
+	// contiguous run of the launch's segments: consecutive segments share Lh
+	// points, which stay in the TMEM stash (TmemReuse), and the CTAs of the
+	// channels of one stretch of interleaved input run side by side and share it
+	// through L2.
+	const int ci = (int)blockIdx.x % p.nchan, jb = (int)blockIdx.x / p.nchan;
+	const int nb = ((int)gridDim.x - ci + p.nchan - 1) / p.nchan; // CTAs of this channel
+	const int run = ((int)p.nseg + nb - 1) / nb;
+	const int s_begin = jb * run, s_end = min ((int)p.nseg, s_begin + run);
+	const int c = p.chan0 + ci;
+	bool prev_inside = false;
+	for (int si = s_begin; si < s_end; ++si) {
 		const long long seg = p.seg0 + si * p.seg_stride;
-		const int       c   = p.chan0 + ci;
 		const long long n0  = seg * p.V - p.Lh; // complex stream index of local index 0
-		int sn = si + gq, cn = ci + gr; // this CTA's next work item
-		if (cn >= p.nchan) {
-			cn -= p.nchan;
-			++sn;
-		}
-		si = sn;
-		ci = cn;
-
-		if (EPI == EPI_POINTS && c != raw_chan) {
-			if (raw_chan >= 0) {
-				// flush the running raw peak of the previous channel
-				float r = cx.rawmax;
-				for (int o = 16; o; o >>= 1) r = fmaxf (r, __shfl_xor_sync (0xffffffffu, r, o));
-				if (lane == 0) atomicMax (p.rawpeak + raw_chan, __float_as_uint (r));
-			}
-			raw_chan  = c;
-			cx.rawmax = 0.f;
-		}
-		if (w + (int)gridDim.x < total && lane == 0) {
-			// pull the next segment towards L2 while this one is transformed: one
-			// bulk prefetch per warp, 16 pieces
-			const long long nn0 = (p.seg0 + sn * p.seg_stride) * p.V - p.Lh;
+		if (si + 1 < s_end && lane == 0 && (SRC == SRC_PLANE || ci == 0)) {
+			// pull the new part of the next segment towards L2 while this one is
+			// transformed: one bulk prefetch per warp, 16 pieces
+			const long long nn0 = n0 + p.seg_stride * p.V + (p.seg_stride == 1 ? p.Lh : 0);
+			const long long npt = p.seg_stride == 1 ? p.V : kM;
 			const char*     pf;
 			long long       nbytes;
 			if (SRC == SRC_PLANE) {
-				pf     = reinterpret_cast<const char*> (p.plane + (long long)(p.chan0 + cn) * p.plane_stride + p.padf + nn0);
-				nbytes = (long long)kM * (long long)sizeof (float2);
+				pf     = reinterpret_cast<const char*> (p.plane + (long long)c * p.plane_stride + p.padf + nn0);
+				nbytes = npt * (long long)sizeof (float2);
 			} else {
 				pf     = reinterpret_cast<const char*> (p.inter + 2 * nn0 * p.C);
-				nbytes = (cn == 0 && nn0 >= 0 && 2 * (nn0 + kM) <= p.n_frames) ? (long long)kM * 2 * p.C * (long long)sizeof (float) : 0;
+				nbytes = (nn0 >= 0 && 2 * (nn0 + npt) <= p.n_frames) ? npt * 2 * p.C * (long long)sizeof (float) : 0;
 			}
 			if (nbytes > 0) {
 				const unsigned piece = (unsigned)(nbytes >> 4) & ~15u;
@@ -473,22 +477,24 @@ __global__ void __launch_bounds__ (kConvThreads, 1) fftconv_kernel (const ConvPa
 			run_segment<EPI> (sm, xch, tb, p, tid, lane, cx, PlaneLoader { p.plane + (long long)c * p.plane_stride + p.padf + n0 });
 		} else {
 			const bool inside = n0 >= 0 && 2 * (n0 + kM) <= p.n_frames;
+			const int  reuse  = (inside && prev_inside && p.seg_stride == 1) ? (p.Lh >> 9) : 0;
+			prev_inside       = inside;
 			if (!inside) {
 				run_segment<EPI> (sm, xch, tb, p, tid, lane, cx, EdgeLoader { p.inter, p.hist, p.n_frames, 2 * n0, p.C, c, 2 * p.Lh });
 			} else if (p.C == 2 && (reinterpret_cast<uintptr_t> (p.inter) & 15) == 0) {
-				run_segment<EPI> (sm, xch, tb, p, tid, lane, cx, Inter2Loader { reinterpret_cast<const float4*> (p.inter) + n0, c });
+				run_segment<EPI> (sm, xch, tb, p, tid, lane, cx, Inter2Loader { reinterpret_cast<const float4*> (p.inter) + n0, c }, reuse);
 			} else if (p.C == 1 && (reinterpret_cast<uintptr_t> (p.inter) & 7) == 0) {
-				run_segment<EPI> (sm, xch, tb, p, tid, lane, cx, Inter1Loader { reinterpret_cast<const float2*> (p.inter) + n0 });
+				run_segment<EPI> (sm, xch, tb, p, tid, lane, cx, Inter1Loader { reinterpret_cast<const float2*> (p.inter) + n0 }, reuse);
 			} else {
-				run_segment<EPI> (sm, xch, tb, p, tid, lane, cx, InterNLoader { p.inter + 2 * n0 * p.C + c, p.C });
+				run_segment<EPI> (sm, xch, tb, p, tid, lane, cx, InterNLoader { p.inter + 2 * n0 * p.C + c, p.C }, reuse);
 			}
 		}
 	}
 
-	if (EPI == EPI_POINTS && raw_chan >= 0) {
+	if (EPI == EPI_POINTS && s_begin < s_end) {
 		float r = cx.rawmax;
 		for (int o = 16; o; o >>= 1) r = fmaxf (r, __shfl_xor_sync (0xffffffffu, r, o));
-		if (lane == 0) atomicMax (p.rawpeak + raw_chan, __float_as_uint (r));
+		if (lane == 0) atomicMax (p.rawpeak + c, __float_as_uint (r));
 	}
 	tmem_free_all (tmem, tid);
 }
