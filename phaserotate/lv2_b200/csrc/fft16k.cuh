@@ -406,8 +406,27 @@ struct GTable { // G4[c * 1024 + row] as built by make_filter_spectrum()
 		for (int c = 0; c < 8; ++c) g[c] = PRK_LDG (G4 + c * 1024 + row);
 	}
 };
-template <class GSrc>
-PRK_HD void mid_pass (float2* sm, GSrc gs, const float2* __restrict__ twm, int t)
+// Two-partition form (FIR longer than M/2 half-taps, i.e. CLI block 32768): the
+// taps are split in two halves of Lp = M/2, the segment advance V equals Lp, so
+// partition 1 of output segment s is partition-1-filter times the spectrum of
+// input segment s - 1:  out_s = IFFT (Z_s G0 + Z_{s-1} G1).  A thread owns the
+// same two spectrum rows in every segment, so Z_{s-1} is thread-private scratch
+// (`scr`, global memory, L2 resident: element (h * 8 + c) * 512 of the thread's
+// base holds chunk c of row t + 512 h).
+//   MID_CONV      one partition (the normal case)
+//   MID_SPECTRUM  forward half only: leave Z in `scr` (first segment of a run)
+//   MID_CONV2     read Z_{s-1} from `scr`, replace it by Z_s, two-partition product
+enum { MID_CONV = 0, MID_SPECTRUM = 1, MID_CONV2 = 2 };
+#if defined(__CUDA_ARCH__)
+#define PRK_LDCG(p) __ldcg (p)
+#define PRK_STCG(p, v) __stcg (p, v)
+#else
+#define PRK_LDCG(p) (*(p))
+#define PRK_STCG(p, v) (*(p) = (v))
+#endif
+template <int MODE = MID_CONV, class GSrc>
+PRK_HD void mid_pass (float2* sm, GSrc gs, const float2* __restrict__ twm, int t, float4* scr = nullptr, const float4* __restrict__ G0 = nullptr,
+                      const float4* __restrict__ G1 = nullptr)
 {
 	const int q2 = t & 31;
 	float2    tw[16];
@@ -418,7 +437,7 @@ PRK_HD void mid_pass (float2* sm, GSrc gs, const float2* __restrict__ twm, int t
 		const int row = t + 512 * h;
 		const int s   = ((row >> 5) ^ row) & 7;
 		float4*   rp  = reinterpret_cast<float4*> (sm + (row << 4));
-		gs.issue (h);
+		if (MODE == MID_CONV) gs.issue (h);
 		float2 u[16];
 #pragma unroll
 		for (int c = 0; c < 8; ++c) {
@@ -429,12 +448,28 @@ PRK_HD void mid_pass (float2* sm, GSrc gs, const float2* __restrict__ twm, int t
 #pragma unroll
 		for (int j = 1; j < 16; ++j) u[j] = cmul (u[j], tw[j]);
 		dft16<-1> (u);
-		float4 g[8];
-		gs.get (g);
+		if (MODE == MID_SPECTRUM) {
 #pragma unroll
-		for (int c = 0; c < 8; ++c) {
-			u[2 * c]     = cmul (u[2 * c], make_float2 (g[c].x, g[c].y));
-			u[2 * c + 1] = cmul (u[2 * c + 1], make_float2 (g[c].z, g[c].w));
+			for (int c = 0; c < 8; ++c) PRK_STCG (scr + (h * 8 + c) * 512, make_float4 (u[2 * c].x, u[2 * c].y, u[2 * c + 1].x, u[2 * c + 1].y));
+			continue;
+		}
+		if (MODE == MID_CONV2) {
+#pragma unroll
+			for (int c = 0; c < 8; ++c) {
+				const float4 pv = PRK_LDCG (scr + (h * 8 + c) * 512);
+				const float4 g0 = PRK_LDG (G0 + c * 1024 + row), g1 = PRK_LDG (G1 + c * 1024 + row);
+				PRK_STCG (scr + (h * 8 + c) * 512, make_float4 (u[2 * c].x, u[2 * c].y, u[2 * c + 1].x, u[2 * c + 1].y));
+				u[2 * c]     = cadd (cmul (u[2 * c], make_float2 (g0.x, g0.y)), cmul (make_float2 (pv.x, pv.y), make_float2 (g1.x, g1.y)));
+				u[2 * c + 1] = cadd (cmul (u[2 * c + 1], make_float2 (g0.z, g0.w)), cmul (make_float2 (pv.z, pv.w), make_float2 (g1.z, g1.w)));
+			}
+		} else {
+			float4 g[8];
+			gs.get (g);
+#pragma unroll
+			for (int c = 0; c < 8; ++c) {
+				u[2 * c]     = cmul (u[2 * c], make_float2 (g[c].x, g[c].y));
+				u[2 * c + 1] = cmul (u[2 * c + 1], make_float2 (g[c].z, g[c].w));
+			}
 		}
 		dft16<+1> (u);
 #pragma unroll

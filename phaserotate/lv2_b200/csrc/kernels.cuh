@@ -49,8 +49,12 @@ struct ConvParams {
 	const float2* G;            // [kM] filter spectrum / kM in MID-pass order (fft16k_tables.h)
 	const float2* tw1;          // [10][512]  W_M^(e a), a = 1..7 | W_M^(8 e b), b = 1..3
 	const float2* tw2;          // [15][32]   W_512^(j q2), j = 1..15
-	int           Lh;           // half taps = L/2 (multiple of 4)
+	int           Lh;           // overlap of consecutive segments = half taps of one partition (multiple of 512)
 	int           V;            // valid complex outputs per segment = kM - Lh
+	int           dl;           // delay of the direct branch in complex points = (all half taps) / 2
+	int           hist_frames;  // SRC_INTER: frames in `hist` (= FIR length)
+	const float2* G1;           // two partitions: spectrum of the second half of the taps (same order as G)
+	float4*       scratch;      // two partitions: [gridDim.x][kM / 2] spectrum of the previous segment, per CTA
 	int           chan0;        // first channel of this launch
 	long long     seg0;         // first segment
 	long long     seg_stride;   // segment index step (1 = contiguous; > 1 = sparse bootstrap sample)
@@ -236,7 +240,7 @@ __device__ __forceinline__ void load_direct (float2 (&zd)[4], const bool (&ok)[4
 template <int EPI, class Loader>
 __device__ __forceinline__ void epilogue (const float2 (&w)[32], const float* xch, uint32_t tb, const ConvParams& p, int tid, int lane, EpiCtx& cx, const Loader& ld)
 {
-	const int dl    = p.Lh >> 1;
+	const int dl    = p.dl;
 	const int warp  = tid >> 5;
 	const int xbase = warp ? (warp - 1) * 32 : 15 * 32 - 1;
 	if (EPI == EPI_POINTS) {
@@ -366,11 +370,11 @@ __device__ __forceinline__ int opaque_tid (const int* tidbuf, int tid)
 }
 
 // One segment: five passes, four shared-memory round trips, epilogue from registers.
-template <int EPI, class Loader>
+template <int EPI, int NP, class Loader>
 __device__ __forceinline__ void run_segment (float2* sm, float* xch, uint32_t tb, const ConvParams& p, int tid, int lane, EpiCtx& cx, const Loader ld, int reuse_rows = 0)
 {
 	const int* tidbuf = reinterpret_cast<const int*> (xch + kXchFloats + 4);
-	if (EPI != EPI_HILBERT && stash_usable (p.Lh >> 1)) {
+	if (EPI != EPI_HILBERT && stash_usable (p.dl)) {
 		p1_forward (sm, p.tw1, opaque_tid (tidbuf, tid), ld, TmemStash { tb }, TmemReuse { tb, reuse_rows, p.V >> 9 });
 		tmem_wait_st ();
 	} else {
@@ -380,7 +384,13 @@ __device__ __forceinline__ void run_segment (float2* sm, float* xch, uint32_t tb
 	// the three middle passes of a block pair stay inside one warp (see p2_block())
 	p2_pass<-1> (sm, opaque_tid (tidbuf, tid));
 	__syncwarp ();
-	mid_pass (sm, GTmem { tb }, p.tw2, opaque_tid (tidbuf, tid));
+	if (NP == 2) {
+		const int t = opaque_tid (tidbuf, tid);
+		mid_pass<MID_CONV2> (sm, GTmem { tb }, p.tw2, t, p.scratch + (size_t)blockIdx.x * (kM / 2) + t, reinterpret_cast<const float4*> (p.G),
+		                     reinterpret_cast<const float4*> (p.G1));
+	} else {
+		mid_pass (sm, GTmem { tb }, p.tw2, opaque_tid (tidbuf, tid));
+	}
 	__syncwarp ();
 	p2_pass<+1> (sm, opaque_tid (tidbuf, tid));
 	__syncthreads ();
@@ -395,13 +405,28 @@ __device__ __forceinline__ void run_segment (float2* sm, float* xch, uint32_t tb
 	epilogue<EPI> (w, xch, tb, p, tid, lane, cx, ld);
 }
 
+// Two partitions: forward transform of the segment before the first one of a run,
+// left in the CTA's scratch (see mid_pass()).
+template <class Loader>
+__device__ __noinline__ void spectrum_only (float2* sm, const float* xch, const float2* tw1, const float2* tw2, float4* scr, int tid, const Loader ld)
+{
+	const int* tidbuf = reinterpret_cast<const int*> (xch + kXchFloats + 4);
+	p1_forward (sm, tw1, opaque_tid (tidbuf, tid), ld);
+	__syncthreads ();
+	p2_pass<-1> (sm, opaque_tid (tidbuf, tid));
+	__syncwarp ();
+	const int t = opaque_tid (tidbuf, tid);
+	mid_pass<MID_SPECTRUM> (sm, GTable { nullptr, 0, 0 }, tw2, t, scr + t);
+	__syncthreads (); // every warp is done reading sm
+}
+
 // ---------------------------------------------------------------------------
 // K1: FFT convolution with fused epilogue.  Persistent: one CTA per SM walks
 // (segment, channel) pairs, channel fastest, so that the CTAs working on the
 // channels of one stretch of interleaved input run at the same time and share
-// it through L2.
+// it through L2.  NP = number of tap partitions (2 only for FIR length 32768).
 // ---------------------------------------------------------------------------
-template <int EPI, int SRC>
+template <int EPI, int SRC, int NP>
 __global__ void __launch_bounds__ (kConvThreads, 1) fftconv_kernel (const ConvParams p)
 {
 	extern __shared__ __align__ (16) float2 sm[];
@@ -442,6 +467,14 @@ __global__ void __launch_bounds__ (kConvThreads, 1) fftconv_kernel (const ConvPa
 	for (int si = s_begin; si < s_end; ++si) {
 		const long long seg = p.seg0 + si * p.seg_stride;
 		const long long n0  = seg * p.V - p.Lh; // complex stream index of local index 0
+		if (NP == 2 && (si == s_begin || p.seg_stride != 1)) {
+			// the scratch does not hold the spectrum of segment seg - 1 yet
+			if (SRC == SRC_PLANE) {
+				spectrum_only (sm, xch, p.tw1, p.tw2, p.scratch + (size_t)blockIdx.x * (kM / 2), tid, PlaneLoader { p.plane + (long long)c * p.plane_stride + p.padf + n0 - p.V });
+			} else {
+				spectrum_only (sm, xch, p.tw1, p.tw2, p.scratch + (size_t)blockIdx.x * (kM / 2), tid, EdgeLoader { p.inter, p.hist, p.n_frames, 2 * (n0 - p.V), p.C, c, p.hist_frames });
+			}
+		}
 		if (si + 1 < s_end && lane == 0 && (SRC == SRC_PLANE || ci == 0)) {
 			// pull the new part of the next segment towards L2 while this one is
 			// transformed: one bulk prefetch per warp, 16 pieces
@@ -474,19 +507,19 @@ __global__ void __launch_bounds__ (kConvThreads, 1) fftconv_kernel (const ConvPa
 		}
 
 		if (SRC == SRC_PLANE) {
-			run_segment<EPI> (sm, xch, tb, p, tid, lane, cx, PlaneLoader { p.plane + (long long)c * p.plane_stride + p.padf + n0 });
+			run_segment<EPI, NP> (sm, xch, tb, p, tid, lane, cx, PlaneLoader { p.plane + (long long)c * p.plane_stride + p.padf + n0 });
 		} else {
 			const bool inside = n0 >= 0 && 2 * (n0 + kM) <= p.n_frames;
 			const int  reuse  = (inside && prev_inside && p.seg_stride == 1) ? (p.Lh >> 9) : 0;
 			prev_inside       = inside;
 			if (!inside) {
-				run_segment<EPI> (sm, xch, tb, p, tid, lane, cx, EdgeLoader { p.inter, p.hist, p.n_frames, 2 * n0, p.C, c, 2 * p.Lh });
+				run_segment<EPI, NP> (sm, xch, tb, p, tid, lane, cx, EdgeLoader { p.inter, p.hist, p.n_frames, 2 * n0, p.C, c, p.hist_frames });
 			} else if (p.C == 2 && (reinterpret_cast<uintptr_t> (p.inter) & 15) == 0) {
-				run_segment<EPI> (sm, xch, tb, p, tid, lane, cx, Inter2Loader { reinterpret_cast<const float4*> (p.inter) + n0, c }, reuse);
+				run_segment<EPI, NP> (sm, xch, tb, p, tid, lane, cx, Inter2Loader { reinterpret_cast<const float4*> (p.inter) + n0, c }, reuse);
 			} else if (p.C == 1 && (reinterpret_cast<uintptr_t> (p.inter) & 7) == 0) {
-				run_segment<EPI> (sm, xch, tb, p, tid, lane, cx, Inter1Loader { reinterpret_cast<const float2*> (p.inter) + n0 }, reuse);
+				run_segment<EPI, NP> (sm, xch, tb, p, tid, lane, cx, Inter1Loader { reinterpret_cast<const float2*> (p.inter) + n0 }, reuse);
 			} else {
-				run_segment<EPI> (sm, xch, tb, p, tid, lane, cx, InterNLoader { p.inter + 2 * n0 * p.C + c, p.C }, reuse);
+				run_segment<EPI, NP> (sm, xch, tb, p, tid, lane, cx, InterNLoader { p.inter + 2 * n0 * p.C + c, p.C }, reuse);
 			}
 		}
 	}

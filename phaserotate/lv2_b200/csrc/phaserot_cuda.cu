@@ -179,7 +179,9 @@ struct phaserot {
 	int            n_sm  = 148;
 	int            C     = 1;
 	int            L     = 0;   // FIR length
-	int            Lh    = 0;   // half taps
+	int            Lh    = 0;   // half taps (odd taps of the FIR)
+	int            NP    = 1;   // tap partitions of the FFT convolution (2 for L = 32768)
+	int            Lp    = 0;   // half taps per partition = overlap of consecutive segments
 	int            V     = 0;   // valid complex outputs per segment
 	int            padf  = 0;   // front pad of a plane (complex elements)
 	int            S     = 2;
@@ -194,7 +196,7 @@ struct phaserot {
 	std::vector<float> taps, lut_s, lut_c;
 	std::vector<float> table; // [C][MS]  == PhaseRotate::_peak
 
-	DevBuf d_G, d_tw, d_g;
+	DevBuf d_G, d_G1, d_scratch, d_tw, d_g;
 	DevBuf d_plane, d_out, d_list, d_stage[2], d_io, d_inter, d_hist;
 	DevBuf d_small; // count[C] | thr2[C] | raw[C] | ramp_len[C] | stats[2 x u64]
 	DevBuf d_cs, d_peaks, d_ramp, d_chancs;
@@ -312,10 +314,19 @@ upload_tables (phaserot* h)
 		g[(size_t)j] = h->taps[(size_t)(2 * j + 1)];
 	}
 	// filter spectrum / M in MID-pass order, twiddles (fft16k_tables.h)
-	const std::vector<float2> G = make_filter_spectrum (g.data (), Lh);
+	const std::vector<float2> G = make_filter_spectrum (g.data (), h->Lp);
 	int rc = h->d_G.ensure (sizeof (float2) * kM);
 	if (rc) return rc;
 	CK (cudaMemcpy (h->d_G.p, G.data (), sizeof (float2) * kM, cudaMemcpyHostToDevice));
+	if (h->NP == 2) {
+		// second half of the taps and the per-CTA spectrum scratch (see mid_pass())
+		const std::vector<float2> G1 = make_filter_spectrum (g.data () + h->Lp, h->Lp);
+		rc = h->d_G1.ensure (sizeof (float2) * kM);
+		if (rc) return rc;
+		CK (cudaMemcpy (h->d_G1.p, G1.data (), sizeof (float2) * kM, cudaMemcpyHostToDevice));
+		rc = h->d_scratch.ensure (sizeof (float2) * kM * (size_t)h->n_sm);
+		if (rc) return rc;
+	}
 	const std::vector<float2> tw = make_twiddles ();
 	rc = h->d_tw.ensure (sizeof (float2) * tw.size ());
 	if (rc) return rc;
@@ -338,18 +349,22 @@ fill_conv_common (phaserot* h, ConvParams& p)
 	p.G            = (const float2*)h->d_G.p;
 	p.tw1          = (const float2*)h->d_tw.p;
 	p.tw2          = p.tw1 + kTwP1Rows * 512;
-	p.Lh           = h->Lh;
+	p.Lh           = h->Lp;
 	p.V            = h->V;
+	p.dl           = h->Lh / 2;
+	p.hist_frames  = h->L;
+	p.G1           = (const float2*)h->d_G1.p;
+	p.scratch      = (float4*)h->d_scratch.p;
 	p.seg_stride   = 1;
 }
 
-template <int EPI, int SRC = SRC_PLANE>
+template <int EPI, int SRC, int NP>
 int
-launch_conv (phaserot* h, const ConvParams& p)
+launch_conv_np (phaserot* h, const ConvParams& p)
 {
 	static bool attr_done = false; // one flag per template instantiation
 	if (!attr_done) {
-		CK (cudaFuncSetAttribute (fftconv_kernel<EPI, SRC>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+		CK (cudaFuncSetAttribute (fftconv_kernel<EPI, SRC, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
 		attr_done = true;
 	}
 	const long long total = p.nseg * p.nchan;
@@ -358,10 +373,17 @@ launch_conv (phaserot* h, const ConvParams& p)
 	}
 	const int grid = (int)std::min<long long> (total, h->n_sm);
 	ProfScope ps (h, EPI == EPI_POINTS ? 0 : 3);
-	fftconv_kernel<EPI, SRC><<<grid, kConvThreads, kSmemBytes, h->stream>>> (p);
+	fftconv_kernel<EPI, SRC, NP><<<grid, kConvThreads, kSmemBytes, h->stream>>> (p);
 	CK (cudaGetLastError ());
 	++h->stats.kernel_launches;
 	return PHASEROT_OK;
+}
+
+template <int EPI, int SRC = SRC_PLANE>
+int
+launch_conv (phaserot* h, const ConvParams& p)
+{
+	return h->NP == 2 ? launch_conv_np<EPI, SRC, 2> (h, p) : launch_conv_np<EPI, SRC, 1> (h, p);
 }
 
 // plane geometry for `m_end` complex outputs per channel
@@ -972,8 +994,8 @@ phaserot_create (phaserot_t** out, const phaserot_cfg_t* cfg)
 	if (S < 1 || S > 1000) {
 		return PHASEROT_E_INVAL;
 	}
-	if (L / 2 > kM / 2) {
-		snprintf (g_last_error, sizeof (g_last_error), "FIR length %d needs %d half-taps; this build supports at most %d", L, L / 2, kM / 2);
+	if (L / 2 > kM) {
+		snprintf (g_last_error, sizeof (g_last_error), "FIR length %d needs %d half-taps; this build supports at most %d", L, L / 2, kM);
 		return PHASEROT_E_UNSUPPORTED;
 	}
 
@@ -1014,7 +1036,9 @@ phaserot_create (phaserot_t** out, const phaserot_cfg_t* cfg)
 	h->C      = cfg->n_channels;
 	h->L      = L;
 	h->Lh     = L / 2;
-	h->V      = kM - h->Lh;
+	h->NP     = h->Lh > kM / 2 ? 2 : 1;
+	h->Lp     = h->Lh / h->NP;
+	h->V      = kM - h->Lp;
 	h->padf   = (h->Lh + 3) & ~3;
 	h->S      = S;
 	h->MS     = 180 * S;
@@ -1078,7 +1102,7 @@ phaserot_destroy (phaserot_t* h)
 	DevGuard                    guard (h->dev);
 	if (h->own_stream) cudaStreamSynchronize (h->own_stream);
 	if (h->copy_stream) cudaStreamSynchronize (h->copy_stream);
-	for (DevBuf* b : { &h->d_G, &h->d_tw, &h->d_g, &h->d_plane, &h->d_out, &h->d_list, &h->d_stage[0], &h->d_stage[1], &h->d_io, &h->d_inter, &h->d_hist, &h->d_small,
+	for (DevBuf* b : { &h->d_G, &h->d_G1, &h->d_scratch, &h->d_tw, &h->d_g, &h->d_plane, &h->d_out, &h->d_list, &h->d_stage[0], &h->d_stage[1], &h->d_io, &h->d_inter, &h->d_hist, &h->d_small,
 	                   &h->d_cs, &h->d_peaks, &h->d_ramp, &h->d_chancs }) {
 		b->release ();
 	}

@@ -52,6 +52,9 @@ SWEEP_CASES = {
     "odd_len_2ch_L1024": (lambda: O.harmonic(48000, 0.5, 2)[:23999], 1024),
     "one_frame_L2048": (lambda: np.array([[0.5, -0.25]], np.float32), 2048),
     "eight_ch_L1024": (lambda: O.harmonic(48000, 0.25, 8), 1024),
+    # FIR length 32768 (192 kHz files, cli:749-755): two tap partitions on the device
+    "harmonic_2ch_L32768": (lambda: O.harmonic(192000, 0.9, 2), 32768),
+    "short_mono_L32768": (lambda: O.pink_noise(5000, 11)[:, None], 32768),
 }
 
 
@@ -211,6 +214,32 @@ def test_full_size_pruned_equals_brute_force_and_shards_combine():
         assert rel(np.maximum(a, h.peaks()), brute) <= 2e-6
 
 
+def test_blksiz_32768_pruned_equals_brute_force_and_shards_combine():
+    """FIR length 32768 (two tap partitions): 2 min stereo at 0.1 deg, same properties as above."""
+    L = 32768
+    x, frames = _device_programme(120.0)
+    frames -= frames % L
+    with capi.Phaserot(n_channels=2, blksiz=L, subsample=10) as h:
+        h.sweep_device(x.data_ptr(), frames)
+        pruned = h.peaks()
+        al = h.shard_align()
+        assert al % L == 0
+        half = (frames // 2) - ((frames // 2) % al)
+        h.reset()
+        h.sweep_shard_device(x.data_ptr(), half, None, True, False)
+        a = h.peaks()
+        hist = x[half - L:half].cpu().numpy()
+        h.reset()
+        h.sweep_shard_device(x[half:].data_ptr(), frames - half, hist, False, True)
+        b = h.peaks()
+    with capi.Phaserot(n_channels=2, blksiz=L, subsample=10, flags=capi.FLAG_NO_PRUNE) as h:
+        h.sweep_device(x.data_ptr(), frames)
+        brute = h.peaks()
+    assert np.array_equal(pruned, brute)
+    assert np.array_equal(np.maximum(a, b), brute)
+    assert np.all(brute[:, 1:] > 0)
+
+
 def test_full_size_render_properties():
     """3 min stereo: angle 0 is a pure delay of blksiz/2; rendering is linear; +90 then the
     matching -90 rotation restores the (twice delayed) input away from DC/Nyquist effects."""
@@ -237,10 +266,12 @@ def test_full_size_render_properties():
 # render
 # ---------------------------------------------------------------------------
 
-@pytest.mark.parametrize("name,L,ang", [("two_sine", 8192, [37, 181]), ("pink", 8192, [180]), ("programme", 2048, [-45, 359]), ("harmonic", 16384, [90, 270, 1])])
+@pytest.mark.parametrize("name,L,ang", [("two_sine", 8192, [37, 181]), ("pink", 8192, [180]), ("programme", 2048, [-45, 359]), ("harmonic", 16384, [90, 270, 1]),
+                                         ("harmonic192", 32768, [33, 300])])
 def test_render_matches_oracle(name, L, ang):
     x = {"two_sine": lambda: O.two_sine(48000, 1.3, 2), "pink": lambda: O.pink_noise(100000, 3)[:, None],
-         "programme": lambda: O.programme(48000, 0.7, 2), "harmonic": lambda: O.harmonic(96000, 0.9, 3)}[name]()
+         "programme": lambda: O.programme(48000, 0.7, 2), "harmonic": lambda: O.harmonic(96000, 0.9, 3),
+         "harmonic192": lambda: O.harmonic(192000, 0.8, 2)}[name]()
     yo = O.oracle_apply(x, L, ang, 1)
     scale = float(np.abs(yo).max())
     with capi.Phaserot(n_channels=x.shape[1], blksiz=L) as h:

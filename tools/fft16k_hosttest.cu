@@ -71,6 +71,45 @@ main (int argc, char** argv)
 	}
 
 	std::vector<float2> sm ((size_t)kM);
+	if (argc > 2) {
+		// two tap partitions (FIR length 32768): Lh = 2 * Lp taps, Lp = kM / 2, stream of kM + Lp points;
+		// segment A = s[0, kM) leaves its spectrum in the scratch, segment B = s[Lp, Lp + kM) is convolved
+		const int Lp = kM / 2, L2 = 2 * Lp;
+		std::vector<float> g2 ((size_t)L2);
+		for (auto& v : g2) v = (float)rand () / RAND_MAX - 0.5f;
+		std::vector<float2> s ((size_t)(kM + Lp));
+		for (auto& v : s) v = make_float2 ((float)rand () / RAND_MAX - 0.5f, (float)rand () / RAND_MAX - 0.5f);
+		const std::vector<float2> G0 = make_filter_spectrum (g2.data (), Lp), G1 = make_filter_spectrum (g2.data () + Lp, Lp);
+		std::vector<float4> scr ((size_t)kM / 2);
+		for (int e = 0; e < kConvThreads; ++e) p1_forward (sm.data (), twp1, e, VecLoader { s.data () });
+		for (int t = 0; t < kConvThreads; ++t) p2_pass<-1> (sm.data (), t);
+		for (int t = 0; t < kConvThreads; ++t) mid_pass<MID_SPECTRUM> (sm.data (), GTable { nullptr, 0, 0 }, twm, t, scr.data () + t);
+		for (int e = 0; e < kConvThreads; ++e) p1_forward (sm.data (), twp1, e, VecLoader { s.data () + Lp });
+		for (int t = 0; t < kConvThreads; ++t) p2_pass<-1> (sm.data (), t);
+		for (int t = 0; t < kConvThreads; ++t) {
+			mid_pass<MID_CONV2> (sm.data (), GTable { nullptr, 0, 0 }, twm, t, scr.data () + t, reinterpret_cast<const float4*> (G0.data ()),
+			                     reinterpret_cast<const float4*> (G1.data ()));
+		}
+		for (int t = 0; t < kConvThreads; ++t) p2_pass<+1> (sm.data (), t);
+		double maxerr = 0.0, maxref = 0.0;
+		for (int e = 0; e < kConvThreads; ++e) {
+			float2 w[32];
+			p1_inverse (sm.data (), twp1, e, w);
+			for (int k = 16; k < 32; ++k) {
+				const int i = e + 512 * k; // valid outputs of B: i >= Lp, stream index Lp + i
+				if ((i % 41) != 0) continue;
+				double re = 0.0, im = 0.0;
+				for (int j = 0; j < L2; ++j) {
+					re += (double)g2[(size_t)j] * s[(size_t)(Lp + i - j)].x;
+					im += (double)g2[(size_t)j] * s[(size_t)(Lp + i - j)].y;
+				}
+				maxerr = std::max (maxerr, std::max (std::fabs (re - w[k].x), std::fabs (im - w[k].y)));
+				maxref = std::max (maxref, std::max (std::fabs (re), std::fabs (im)));
+			}
+		}
+		printf ("two partitions  max abs err %.3e  max |ref| %.3e  rel %.3e\n", maxerr, maxref, maxerr / maxref);
+		return (maxerr / maxref < 2e-6 && conflicts == 0) ? 0 : 1;
+	}
 	for (int e = 0; e < kConvThreads; ++e) p1_forward (sm.data (), twp1, e, VecLoader { z.data () });
 	for (int t = 0; t < kConvThreads; ++t) p2_pass<-1> (sm.data (), t);
 	for (int t = 0; t < kConvThreads; ++t) mid_pass (sm.data (), GTable { reinterpret_cast<const float4*> (G.data ()), t, 0 }, twm, t);
