@@ -32,7 +32,7 @@ extern "C" {
 #define PHASEROT_API __attribute__ ((visibility ("default")))
 #endif
 
-#define PHASEROT_ABI_VERSION 1
+#define PHASEROT_ABI_VERSION 2
 
 typedef struct phaserot phaserot_t;
 
@@ -69,7 +69,27 @@ typedef struct phaserot_cfg {
 	int32_t  subsample;   /* angle grid: MAXSAMPLE = 180 * subsample; 0 -> 2 = the reference grid (cli:38-39) */
 	int32_t  device;      /* CUDA device ordinal, -1 = current device */
 	uint32_t flags;       /* PHASEROT_FLAG_* */
+	int32_t  oversample;  /* analysis peak detector: 0 or 1 = digital (sample) peak like the reference
+	                       * (cli:98-121, cli/dsp_peak_calc.h); 2 or 4 = oversampled true-peak, see below */
 } phaserot_cfg_t;
+
+/*
+ * Oversampled true-peak (cfg.oversample = 2 or 4) is NOT a reference feature
+ * (the reference measures the digital peak only) - parity is
+ * unpinned and the definition below is this library's own, restated on the CPU
+ * in oracle/phaserot_oracle.c (pro_cli_analyze_tp) for the tests.
+ *
+ * Interpolator: the 48-tap, 4-phase polyphase FIR of ITU-R BS.1770-4 Annex 2,
+ *     s^[t, ph] = sum_{k = 0..11} c[ph][k] * s[t - k],   ph = 0..3
+ * (oversample 2 uses phases 0 and 2).  Interpolation is linear, so the pair
+ * (x_d, H) is interpolated once and every angle is evaluated on the result:
+ *     peak[c][a] = max over the samples t the reference examines of
+ *                  max ( |ca x_d[t] + sa H[t]|,  max_ph |ca x_d^[t, ph] + sa H^[t, ph]| )
+ * i.e. the digital peak is always included (true-peak >= digital peak), x_d
+ * carries the first-block rule (cli:418-419: zero for t < blksiz), and samples
+ * before the stream start are zero.  For un-wrapped angle 0 (cli:413-414) the
+ * same detector runs on the raw input.
+ */
 
 /* ---- lifetime ---------------------------------------------------------- */
 
@@ -215,8 +235,9 @@ PHASEROT_API int phaserot_reset_stats (phaserot_t* h);
 /* Per-kernel device times, measured with CUDA events recorded on the handle's
  * stream around every launch while profiling is on (bench.py's roofline leg).
  * Index: 0 fftconv+filter (sweep), 1 angle sweep, 2 deinterleave/interleave,
- * 3 fftconv+rotate (render), 4 direct FIR (plugin small calls), 5 other. */
-#define PHASEROT_NKERNELS 6
+ * 3 fftconv+rotate (render), 4 direct FIR (plugin small calls), 5 other,
+ * 6 true-peak sweep front end (fftconv -> Hilbert branch, interpolate + filter). */
+#define PHASEROT_NKERNELS 7
 typedef struct phaserot_ktimes {
 	double   ms[PHASEROT_NKERNELS];
 	uint64_t launches[PHASEROT_NKERNELS];

@@ -332,6 +332,134 @@ pro_cli_analyze (const float* interleaved, int64_t n_frames, int n_chn, int blks
 	pro_cli_analyze_shard (interleaved, n_frames, n_chn, blksiz, subsample, NULL, 1, 1, ang_start, ang_end, ang_stride, only_chn, peaks);
 }
 
+/*
+ * Oversampled true-peak variant of the analysis pass.  NOT a reference feature:
+ * the reference measures the digital peak only (cli:98-121), so there is
+ * nothing to pin this against - "parity unpinned".  It restates the definition
+ * in include/phaserot_cuda.h so that the GPU path has an independent checker:
+ *
+ *   interpolator  ITU-R BS.1770-4 Annex 2, 48 taps in 4 phases of 12,
+ *                 s^[t, ph] = sum_k c[ph][k] s[t - k]   (oversample 2: phases 0, 2)
+ *   pair          p[t] = (xq[t], H[t]),  xq[t] = x[t - L/2], forced to 0 for
+ *                 t < L when the first-block rule applies (cli:418-419)
+ *   peak[c][a]    max over the samples the reference examines (block / angle
+ *                 bookkeeping exactly as pro_cli_analyze_shard) of
+ *                 max (|ca xq + sa H|, max_ph |ca xq^ + sa H^|)
+ *   un-wrapped angle 0 (cli:413-414): the same detector on the raw input block.
+ */
+static const float tp_c0[12] = { 0.0017089843750f, 0.0109863281250f, -0.0196533203125f, 0.0332031250000f, -0.0594482421875f, 0.1373291015625f,
+	                             0.9721679687500f, -0.1022949218750f, 0.0476074218750f, -0.0266113281250f, 0.0148925781250f, -0.0083007812500f };
+static const float tp_c1[12] = { -0.0291748046875f, 0.0292968750000f, -0.0517578125000f, 0.0891113281250f, -0.1665039062500f, 0.4650878906250f,
+	                             0.7797851562500f, -0.2003173828125f, 0.1015625000000f, -0.0582275390625f, 0.0330810546875f, -0.0189208984375f };
+
+static float
+tp_coef (int ph, int k)
+{
+	return ph == 0 ? tp_c0[k] : ph == 1 ? tp_c1[k] : ph == 2 ? tp_c1[11 - k] : tp_c0[11 - k];
+}
+
+/* s points at time 0 of an array that is readable from index -11 */
+static float
+tp_interp (const float* s, int64_t t, int ph)
+{
+	float a = 0.f;
+	for (int k = 0; k < 12; ++k) {
+		a = fmaf (tp_coef (ph, k), s[t - k], a);
+	}
+	return a;
+}
+
+void
+pro_cli_analyze_tp_shard (const float* interleaved, int64_t n_frames, int n_chn, int blksiz, int subsample, int oversample,
+                          const float* hist, int first, int last,
+                          int ang_start, int ang_end, int ang_stride, int only_chn, float* peaks)
+{
+	const int     L         = blksiz;
+	const int     D         = L / 2;
+	const int     maxsample = 180 * subsample;
+	const int64_t B         = last ? (n_frames + L - 1) / L : n_frames / L;
+	const int64_t n_blocks  = last ? B + 1 : B;
+	const int64_t n_pad     = n_blocks * (int64_t)L;
+	const int     nph       = oversample == 4 ? 4 : 2;
+	const int     phs[4]    = { 0, oversample == 4 ? 1 : 2, 2, 3 };
+
+	float* lut_s = (float*)malloc (sizeof (float) * (size_t)maxsample);
+	float* lut_c = (float*)malloc (sizeof (float) * (size_t)maxsample);
+	float* taps  = (float*)malloc (sizeof (float) * (size_t)L);
+	pro_sincos_lut (subsample, lut_s, lut_c);
+	pro_fir_taps (L, taps);
+
+	/* arrays indexed [L + t], t = shard time; L frames of history in front */
+	float* xz = (float*)calloc ((size_t)(n_pad + L), sizeof (float)); /* raw input */
+	float* xq = (float*)calloc ((size_t)(n_pad + L), sizeof (float)); /* delayed direct branch incl. first-block rule */
+	float* H  = (float*)malloc (sizeof (float) * (size_t)(n_pad + L));
+	/* interpolated [ph][t], t in [0, n_pad) */
+	float* xi = (float*)malloc (sizeof (float) * (size_t)n_pad * 4);
+	float* qi = (float*)malloc (sizeof (float) * (size_t)n_pad * 4);
+	float* hi = (float*)malloc (sizeof (float) * (size_t)n_pad * 4);
+
+	const int c0 = only_chn < 0 ? 0 : only_chn;
+	const int c1 = only_chn < 0 ? n_chn : only_chn + 1;
+
+	for (int c = c0; c < c1; ++c) {
+		memset (xz, 0, sizeof (float) * (size_t)(n_pad + L));
+		for (int i = 0; i < L; ++i) {
+			xz[i] = hist ? hist[(size_t)i * n_chn + c] : 0.f;
+		}
+		for (int64_t t = 0; t < n_frames; ++t) {
+			xz[L + t] = interleaved[t * n_chn + c];
+		}
+		pro_hilbert_fir (xz, n_frames + L, taps, L, H, n_pad + L);
+		/* cli:418-419: in the first block of a stream the cos term sees zero history */
+		const int64_t t_zero = (first && B > 0) ? L : -(int64_t)L;
+		for (int64_t t = -(int64_t)L; t < n_pad; ++t) {
+			xq[L + t] = (t >= t_zero && t - D >= -(int64_t)L) ? xz[L + t - D] : 0.f;
+		}
+		for (int p = 0; p < nph; ++p) {
+			for (int64_t t = 0; t < n_pad; ++t) {
+				xi[(size_t)p * n_pad + t] = tp_interp (xz + L, t, phs[p]);
+				qi[(size_t)p * n_pad + t] = tp_interp (xq + L, t, phs[p]);
+				hi[(size_t)p * n_pad + t] = tp_interp (H + L, t, phs[p]);
+			}
+		}
+		float* pk = peaks + (size_t)c * maxsample;
+
+		for (int64_t n = 0; n < n_blocks; ++n) {
+			const int     start = (first && n == 0 && B > 0);
+			const int64_t tb    = n * (int64_t)L;
+			int           angle = ang_start;
+			while (angle <= ang_end) {
+				const int a = ((angle % maxsample) + maxsample) % maxsample;
+				if (angle == 0) {
+					pk[a] = peak_abs (xz + L + tb, L, pk[a]);
+					for (int p = 0; p < nph; ++p) {
+						pk[a] = peak_abs (xi + (size_t)p * n_pad + tb, L, pk[a]);
+					}
+				} else {
+					const int64_t o = start ? D : 0, len = start ? D : L;
+					pk[a] = rotated_peak (xq + L + tb + o, H + L + tb + o, len, pk[a], lut_s[a], lut_c[a]);
+					for (int p = 0; p < nph; ++p) {
+						pk[a] = rotated_peak (qi + (size_t)p * n_pad + tb + o, hi + (size_t)p * n_pad + tb + o, len, pk[a], lut_s[a], lut_c[a]);
+					}
+				}
+				angle += ang_stride;
+				if (angle >= ang_end) {
+					break;
+				}
+			}
+		}
+	}
+	free (hi);
+	free (qi);
+	free (xi);
+	free (H);
+	free (xq);
+	free (xz);
+	free (taps);
+	free (lut_c);
+	free (lut_s);
+}
+
 /* ------------------------------------------------------------------------- */
 /* CLI render                                                                */
 /* ------------------------------------------------------------------------- */

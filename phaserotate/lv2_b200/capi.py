@@ -16,7 +16,7 @@ E_INVAL, E_NO_DEVICE, E_CUDA, E_NOMEM, E_UNSUPPORTED, E_STATE = -1, -2, -3, -4, 
 MODE_CLI, MODE_PLUGIN = 0, 1
 FLAG_NO_FIRST_BLOCK_QUIRK = 1
 FLAG_NO_PRUNE = 2
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 SYMBOLS = [
     "phaserot_create", "phaserot_destroy", "phaserot_reset", "phaserot_set_stream",
@@ -34,6 +34,7 @@ class Cfg(C.Structure):
     _fields_ = [
         ("abi_version", C.c_uint32), ("mode", C.c_int32), ("n_channels", C.c_int32), ("blksiz", C.c_int32),
         ("sample_rate", C.c_double), ("subsample", C.c_int32), ("device", C.c_int32), ("flags", C.c_uint32),
+        ("oversample", C.c_int32),
     ]
 
 
@@ -42,8 +43,8 @@ class Stats(C.Structure):
                 ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
 
 
-NKERNELS = 6
-KERNEL_NAMES = ["fftconv_filter", "sweep", "deinterleave", "fftconv_render", "fir_direct", "other"]
+NKERNELS = 7
+KERNEL_NAMES = ["fftconv_filter", "sweep", "deinterleave", "fftconv_render", "fir_direct", "other", "truepeak_filter"]
 
 
 class KTimes(C.Structure):
@@ -118,12 +119,12 @@ def _ptr(a):
 class Phaserot:
     """Thin RAII wrapper: one libphaserot_cuda handle."""
 
-    def __init__(self, mode=MODE_CLI, n_channels=1, blksiz=8192, sample_rate=48000.0, subsample=2, device=-1, flags=0):
+    def __init__(self, mode=MODE_CLI, n_channels=1, blksiz=8192, sample_rate=48000.0, subsample=2, device=-1, flags=0, oversample=0):
         self._lib = load()
         self._h = C.c_void_p()
         self.n_channels, self.blksiz, self.subsample, self.mode = n_channels, blksiz, subsample or 2, mode
         self.maxsample = 180 * self.subsample
-        cfg = Cfg(ABI_VERSION, mode, n_channels, blksiz, float(sample_rate), subsample, device, flags)
+        cfg = Cfg(ABI_VERSION, mode, n_channels, blksiz, float(sample_rate), subsample, device, flags, oversample)
         rc = self._lib.phaserot_create(C.byref(self._h), C.byref(cfg))
         if rc != OK:
             self._h = C.c_void_p()

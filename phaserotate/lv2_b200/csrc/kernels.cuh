@@ -76,6 +76,7 @@ struct ConvParams {
 	const float2* ramp;         // [n_chan][ramp_stride] per-sample (ca, sa) for t < ramp_len[c]
 	long long     ramp_stride;
 	const int*    ramp_len;     // [n_chan] (in samples, even) or nullptr
+	int           out_compact;  // EPI_HILBERT: segment j of the launch writes its V outputs at out[8 + j V ..) (true-peak staging)
 };
 
 // Segment input loaders: z[n0 + idx] for the first forward pass and the direct
@@ -170,7 +171,7 @@ __device__ __forceinline__ void append_points (float2* lst, unsigned* cnt, bool 
 // Epilogue state shared by the loader-specific instantiations.
 struct EpiCtx {
 	int       c, i_hi, i_skip, i_zero;
-	long long mbase;
+	long long mbase, obase; // complex stream index / output index of local index 0
 	float     rawmax;
 };
 
@@ -316,7 +317,7 @@ __device__ __forceinline__ void epilogue (const float2 (&w)[32], const float* xc
 		}
 		cx.rawmax = rawmax;
 	} else {
-		float2*      outc = p.out + (cx.mbase + (long long)cx.c * p.out_stride);
+		float2*      outc = p.out + (cx.obase + (long long)cx.c * p.out_stride);
 		const float2 cs   = (EPI == EPI_RENDER) ? p.cs[cx.c] : make_float2 (0.f, 1.f);
 		const int    rlen = (EPI == EPI_RENDER && p.ramp_len) ? p.ramp_len[cx.c] : 0;
 #pragma unroll
@@ -499,6 +500,7 @@ __global__ void __launch_bounds__ (kConvThreads, 1) fftconv_kernel (const ConvPa
 		// local bounds of the output regions (clamped to the segment)
 		cx.c     = c;
 		cx.mbase = n0;
+		cx.obase = p.out_compact ? (long long)si * p.V - p.Lh + 8 : n0;
 		{
 			const long long hi = p.m_end - n0, sk = p.m_skip - n0, ze = p.m_zero - n0;
 			cx.i_hi   = hi >= kM ? kM : (hi <= p.Lh ? p.Lh : (int)hi);
@@ -725,6 +727,176 @@ __global__ void __launch_bounds__ (128) fir_direct_kernel (const float* __restri
 		const float2 cs = (o0 + i) < fc.rlen[c] ? pre[(long long)c * pre_stride + o0 + i] : fc.cs[c];
 		out[(long long)c * out_stride + o0 + i] = __fadd_rn (__fmul_rn (cs.x, xd), __fmul_rn (cs.y, h));
 	}
+}
+
+// ---------------------------------------------------------------------------
+// Oversampled true-peak front end of the sweep (cfg.oversample = 2 or 4; not a
+// reference feature, definition in include/phaserot_cuda.h).  The FFT kernel
+// leaves the Hilbert branch H of one launch in `H` (EPI_HILBERT, compact
+// layout: 16 floats of carry from the previous launch, then 2 V samples per
+// segment); this kernel forms the pairs p[t] = (x_d[t], H[t]), interpolates
+// both components with the BS.1770-4 Annex 2 polyphase FIR
+//     p^[t, ph] = sum_{k < 12} c[ph][k] p[t - k]
+// and sends p[t] and every p^[t, ph] through the same exact radius filter and
+// survivor list as the digital sweep, so sweep_kernel and threshold_kernel are
+// shared.  grid = (tiles of 1024 samples, channels), 256 threads x 4 samples.
+// ---------------------------------------------------------------------------
+constexpr int kTpTile  = 1024;
+constexpr int kTpHalo  = 12; // 11 past samples are needed; 12 keeps the 16-byte alignment of a thread's window
+constexpr int kTpCarry = 16; // floats kept in front of H from the previous launch
+
+// ITU-R BS.1770-4 Annex 2, table "filter coefficients" (all multiples of 2^-13: exact in fp32)
+PRK_HD constexpr float tp_coef (int ph, int k)
+{
+	constexpr float c0[12] = { 0.0017089843750f, 0.0109863281250f, -0.0196533203125f, 0.0332031250000f, -0.0594482421875f, 0.1373291015625f,
+		                       0.9721679687500f, -0.1022949218750f, 0.0476074218750f, -0.0266113281250f, 0.0148925781250f, -0.0083007812500f };
+	constexpr float c1[12] = { -0.0291748046875f, 0.0292968750000f, -0.0517578125000f, 0.0891113281250f, -0.1665039062500f, 0.4650878906250f,
+		                       0.7797851562500f, -0.2003173828125f, 0.1015625000000f, -0.0582275390625f, 0.0330810546875f, -0.0189208984375f };
+	return ph == 0 ? c0[k] : ph == 1 ? c1[k] : ph == 2 ? c1[11 - k] : c0[11 - k];
+}
+
+struct TpParams {
+	const float* inter;       // interleaved frames, frame 0 = stream position 0
+	const float* hist;        // frames [-hist_frames, 0) or nullptr (silence)
+	long long    n_frames;
+	int          C, hist_frames;
+	const float* H;           // [channel][h_stride]: kTpCarry floats, then launch-compact samples
+	long long    h_stride;
+	int          chan0;
+	long long    seg0, seg_stride;
+	int          V2;          // samples per segment (2 V)
+	int          D;           // delay of the direct branch in samples (L / 2)
+	long long    t_skip;      // t <  t_skip : not examined            (first-block rule, cli:418-419)
+	long long    t_zero;      // t <  t_zero : direct branch forced to 0
+	long long    t_end;       // samples exist for t < t_end
+	int          os;          // 2 or 4
+	float2*      list;
+	long long    list_stride;
+	unsigned*    count;
+	const float* thr2;
+	unsigned*    rawpeak;
+};
+
+__device__ __forceinline__ float tp_input_at (const TpParams& p, int c, long long f)
+{
+	if (f >= 0) return f < p.n_frames ? __ldg (p.inter + f * p.C + c) : 0.f;
+	return (p.hist && f >= -(long long)p.hist_frames) ? __ldg (p.hist + (p.hist_frames + f) * p.C + c) : 0.f;
+}
+
+template <int PH>
+__device__ __forceinline__ float tp_interp (const float (&s)[16], int n)
+{
+	float a = 0.f;
+#pragma unroll
+	for (int k = 0; k < 12; ++k) a = fmaf (tp_coef (PH, k), s[12 + n - k], a);
+	return a;
+}
+
+__global__ void __launch_bounds__ (256) truepeak_kernel (const TpParams p)
+{
+	__shared__ __align__ (16) float sh[kTpTile + kTpHalo], sx[kTpTile + kTpHalo], sq[kTpTile + kTpHalo];
+	const int       c    = p.chan0 + blockIdx.y;
+	const int       tps  = p.V2 / kTpTile; // tiles per segment
+	const int       si   = blockIdx.x / tps, tile = blockIdx.x - si * tps;
+	const long long u0   = (long long)si * p.V2 + (long long)tile * kTpTile;                        // launch-compact index
+	const long long t0   = (p.seg0 + si * p.seg_stride) * (long long)p.V2 + (long long)tile * kTpTile; // stream time
+	if (t0 >= p.t_end) return;
+	// the 11 samples of H before the tile: inside the segment, in the previous
+	// segment of a contiguous launch, or in the carry of the previous launch; a
+	// sparse (bootstrap) launch has no predecessor, its first 11 samples per
+	// segment are left to the contiguous passes
+	const bool   head_ok = p.seg_stride == 1 || tile > 0;
+	const float* Hc      = p.H + (long long)c * p.h_stride + kTpCarry + u0 - kTpHalo;
+	const bool   q1      = t0 - kTpHalo < p.t_zero; // tile touches the forced-zero region of the direct branch
+	for (int i = threadIdx.x; i < kTpTile + kTpHalo; i += blockDim.x) {
+		const long long t = t0 - kTpHalo + i;
+		const float     x = tp_input_at (p, c, t - p.D);
+		sh[i]             = (head_ok || i >= kTpHalo) ? Hc[i] : 0.f;
+		sx[i]             = x;
+		sq[i]             = t < p.t_zero ? 0.f : x;
+	}
+	__syncthreads ();
+
+	const int j = threadIdx.x;
+	float     hs[16], xs[16], qs[16];
+	{
+		const float4* h4 = reinterpret_cast<const float4*> (sh) + j;
+		const float4* x4 = reinterpret_cast<const float4*> (sx) + j;
+		const float4* q4 = reinterpret_cast<const float4*> (sq) + j;
+#pragma unroll
+		for (int v = 0; v < 4; ++v) {
+			const float4 a = h4[v], b = x4[v];
+			hs[4 * v] = a.x, hs[4 * v + 1] = a.y, hs[4 * v + 2] = a.z, hs[4 * v + 3] = a.w;
+			xs[4 * v] = b.x, xs[4 * v + 1] = b.y, xs[4 * v + 2] = b.z, xs[4 * v + 3] = b.w;
+			if (q1) {
+				const float4 q = q4[v];
+				qs[4 * v] = q.x, qs[4 * v + 1] = q.y, qs[4 * v + 2] = q.z, qs[4 * v + 3] = q.w;
+			} else {
+				qs[4 * v] = b.x, qs[4 * v + 1] = b.y, qs[4 * v + 2] = b.z, qs[4 * v + 3] = b.w;
+			}
+		}
+	}
+	const float    thr2 = p.thr2[c];
+	float2*        lst  = p.list + (long long)c * p.list_stride;
+	unsigned*      cnt  = p.count + c;
+	const int      lane = threadIdx.x & 31;
+	float          rawmax = 0.f;
+#pragma unroll
+	for (int n = 0; n < 4; ++n) {
+		const long long t  = t0 + 4 * j + n;
+		const bool      in = t < p.t_end;
+		const bool      ex = in && t >= p.t_skip && (head_ok || 4 * j + n >= kTpHalo - 1);
+		float2 pt[5];
+		float  xr[5];
+		pt[0] = make_float2 (qs[12 + n], hs[12 + n]);
+		xr[0] = xs[12 + n];
+		pt[1] = make_float2 (tp_interp<0> (qs, n), tp_interp<0> (hs, n));
+		pt[3] = make_float2 (tp_interp<2> (qs, n), tp_interp<2> (hs, n));
+		xr[1] = q1 ? tp_interp<0> (xs, n) : pt[1].x;
+		xr[3] = q1 ? tp_interp<2> (xs, n) : pt[3].x;
+		if (p.os == 4) {
+			pt[2] = make_float2 (tp_interp<1> (qs, n), tp_interp<1> (hs, n));
+			pt[4] = make_float2 (tp_interp<3> (qs, n), tp_interp<3> (hs, n));
+			xr[2] = q1 ? tp_interp<1> (xs, n) : pt[2].x;
+			xr[4] = q1 ? tp_interp<3> (xs, n) : pt[4].x;
+		} else {
+			pt[2] = pt[4] = make_float2 (0.f, 0.f);
+			xr[2] = xr[4] = 0.f;
+		}
+		unsigned keep = 0;
+#pragma unroll
+		for (int q = 0; q < 5; ++q) {
+			if (in) rawmax = fmaxf (rawmax, fabsf (xr[q]));
+			if (ex && fmaf (pt[q].x, pt[q].x, pt[q].y * pt[q].y) >= thr2 && (p.os == 4 || !(q == 2 || q == 4))) keep |= 1u << q;
+		}
+		if (__any_sync (0xffffffffu, keep != 0)) {
+			// one atomic per warp: exclusive prefix sum of the per-lane survivor counts
+			const int nk  = __popc (keep);
+			int       inc = nk;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) {
+				const int v = __shfl_up_sync (0xffffffffu, inc, o);
+				if (lane >= o) inc += v;
+			}
+			unsigned base = 0;
+			if (lane == 31) base = atomicAdd (cnt, (unsigned)inc);
+			base          = __shfl_sync (0xffffffffu, base, 31);
+			unsigned pos  = base + (unsigned)(inc - nk);
+#pragma unroll
+			for (int q = 0; q < 5; ++q) {
+				if (keep & (1u << q)) lst[pos++] = pt[q];
+			}
+		}
+	}
+	for (int o = 16; o; o >>= 1) rawmax = fmaxf (rawmax, __shfl_xor_sync (0xffffffffu, rawmax, o));
+	if (lane == 0 && rawmax > 0.f) atomicMax (p.rawpeak + c, __float_as_uint (rawmax));
+}
+
+// last kTpCarry floats of a contiguous launch's H -> front of the buffer, for the next launch
+__global__ void tp_carry_kernel (float* H, long long h_stride, int chan0, long long n_samples)
+{
+	float* Hc = H + (long long)(chan0 + blockIdx.x) * h_stride;
+	if (threadIdx.x < kTpCarry) Hc[threadIdx.x] = Hc[kTpCarry + n_samples - kTpCarry + threadIdx.x];
 }
 
 } // namespace prk

@@ -200,6 +200,9 @@ struct phaserot {
 	DevBuf d_plane, d_out, d_list, d_stage[2], d_io, d_inter, d_hist;
 	DevBuf d_small; // count[C] | thr2[C] | raw[C] | ramp_len[C] | stats[2 x u64]
 	DevBuf d_cs, d_peaks, d_ramp, d_chancs;
+	DevBuf d_tpH; // true-peak staging of the Hilbert branch: [C][tp_stride] floats
+	long long tp_stride = 0;
+	int       OS        = 1; // 1 = digital peak, 2 / 4 = oversampled true-peak
 	PinBuf h_stage[2], h_res, h_io;
 	long long plane_stride = 0, out_stride = 0, list_stride = 0;
 
@@ -372,7 +375,7 @@ launch_conv_np (phaserot* h, const ConvParams& p)
 		return PHASEROT_OK;
 	}
 	const int grid = (int)std::min<long long> (total, h->n_sm);
-	ProfScope ps (h, EPI == EPI_POINTS ? 0 : 3);
+	ProfScope ps (h, EPI == EPI_POINTS ? 0 : EPI == EPI_HILBERT ? 6 : 3);
 	fftconv_kernel<EPI, SRC, NP><<<grid, kConvThreads, kSmemBytes, h->stream>>> (p);
 	CK (cudaGetLastError ());
 	++h->stats.kernel_launches;
@@ -612,9 +615,19 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 	// survivor list: one launch covers at most `segs_max` segments per channel
 	const int       nchan    = c1 - c0;
 	const long long segs_max = std::max<long long> (1, ((long long)h->n_sm * 8) / nchan);
-	h->list_stride           = std::min (segs_max, std::max<long long> (nseg, 1)) * h->V * 2;
+	const long long segs_cap = std::min (segs_max, std::max<long long> (nseg, 1));
+	const int       OS       = h->OS;
+	h->list_stride           = segs_cap * h->V * 2 * (OS > 1 ? OS + 1 : 1); // true-peak: the sample and OS interpolated points
 	rc                       = h->d_list.ensure ((size_t)h->list_stride * h->C * sizeof (float2));
 	if (rc) return rc;
+	if (OS > 1) {
+		h->tp_stride = (kTpCarry + segs_cap * h->V * 2 + 3) & ~3LL;
+		rc           = h->d_tpH.ensure (sizeof (float) * (size_t)h->tp_stride * h->C);
+		if (rc) return rc;
+		for (int c = c0; c < c1; ++c) { // samples before the stream start are zero
+			CK (cudaMemsetAsync ((float*)h->d_tpH.p + (long long)c * h->tp_stride, 0, sizeof (float) * kTpCarry, h->stream));
+		}
+	}
 
 	h->pend_idx = idx;
 	h->pend_raw = raw;
@@ -647,13 +660,67 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 	const long long wave     = std::max<long long> (1, (h->n_sm + nchan - 1) / nchan); // segments per channel in one wave
 	bool            booted   = thr_mode != 1;
 
+	TpParams tp;
+	memset (&tp, 0, sizeof (tp));
+	if (OS > 1) {
+		p.out         = (float2*)h->d_tpH.p;
+		p.out_stride  = h->tp_stride / 2;
+		p.out_compact = 1;
+		tp.hist        = d_hist;
+		tp.n_frames    = n_frames;
+		tp.C           = h->C;
+		tp.hist_frames = h->L;
+		tp.H           = (const float*)h->d_tpH.p;
+		tp.h_stride    = h->tp_stride;
+		tp.chan0       = c0;
+		tp.V2          = 2 * h->V;
+		tp.D           = h->L / 2;
+		tp.t_skip      = 2 * p.m_skip;
+		tp.t_zero      = 2 * p.m_zero;
+		tp.t_end       = t_end;
+		tp.os          = OS;
+		tp.list        = p.list;
+		tp.list_stride = p.list_stride;
+		tp.count       = p.count;
+		tp.thr2        = p.thr2;
+		tp.rawpeak     = p.rawpeak;
+	}
+	// true-peak: Hilbert branch of the launch -> staging, carry of the last samples to the next launch
+	auto tp_carry = [&] (long long n) -> int {
+		ProfScope ps (h, 5);
+		tp_carry_kernel<<<nchan, 32, 0, h->stream>>> ((float*)h->d_tpH.p, h->tp_stride, c0, n * 2 * h->V);
+		CK (cudaGetLastError ());
+		++h->stats.kernel_launches;
+		return PHASEROT_OK;
+	};
+
 	// one conv launch + sweep of its survivors + new filter radius
 	auto run_launch = [&] (long long s0, long long stride, long long n) -> int {
 		p.seg0       = s0;
 		p.seg_stride = stride;
 		p.nseg       = n;
-		int r        = launch_conv<EPI_POINTS, SRC_INTER> (h, p);
-		if (r) return r;
+		int r;
+		if (OS > 1) {
+			r = launch_conv<EPI_HILBERT, SRC_INTER> (h, p);
+			if (r) return r;
+			tp.inter      = p.inter;
+			tp.seg0       = s0;
+			tp.seg_stride = stride;
+			{
+				ProfScope  ps (h, 6);
+				const dim3 grid ((unsigned)(n * (tp.V2 / kTpTile)), (unsigned)nchan);
+				truepeak_kernel<<<grid, 256, 0, h->stream>>> (tp);
+				CK (cudaGetLastError ());
+				++h->stats.kernel_launches;
+			}
+			if (stride == 1) {
+				r = tp_carry (n);
+				if (r) return r;
+			}
+		} else {
+			r = launch_conv<EPI_POINTS, SRC_INTER> (h, p);
+			if (r) return r;
+		}
 		if (A > 0) {
 			r = launch_sweep (h, A, c0, nchan);
 			if (r) return r;
@@ -665,6 +732,21 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 		CK (cudaGetLastError ());
 		++h->stats.kernel_launches;
 		return PHASEROT_OK;
+	};
+
+	// true-peak on a continued stream: the interpolator reaches 11 samples back,
+	// so the Hilbert branch just before the stream position 0 is needed once: one
+	// extra segment ending there (it reads history only) seeds the carry.  With L
+	// frames of history its last samples lack taps L-16.. of the window edge,
+	// which are below 1e-9 (Hann), far inside fp32 rounding of H.
+	auto tp_head = [&] () -> int {
+		if (OS <= 1 || !d_hist) return PHASEROT_OK;
+		p.seg0       = -1;
+		p.seg_stride = 1;
+		p.nseg       = 1;
+		const int r  = launch_conv<EPI_HILBERT, SRC_INTER> (h, p);
+		if (r) return r;
+		return tp_carry (1);
 	};
 
 	auto process_ready = [&] (bool final) -> int {
@@ -699,6 +781,8 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 	if (src_is_device) {
 		p.inter      = src;
 		frames_ready = n_frames;
+		rc           = tp_head ();
+		if (rc) return rc;
 		rc           = process_ready (true);
 		if (rc) return rc;
 	} else {
@@ -707,6 +791,8 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 		rc = h->d_inter.ensure (std::max<size_t> (sizeof (float) * (size_t)n_frames * h->C, 16));
 		if (rc) return rc;
 		p.inter = (const float*)h->d_inter.p;
+		rc      = tp_head ();
+		if (rc) return rc;
 		const long long chunk_frames = std::max<long long> (2, ((8LL << 20) / h->C) & ~1LL); // ~32 MB per chunk
 		cudaPointerAttributes at;
 		const bool pinned = (cudaPointerGetAttributes (&at, src) == cudaSuccess) && (at.type == cudaMemoryTypeHost);
@@ -750,7 +836,7 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 		rc = process_ready (true);
 		if (rc) return rc;
 	}
-	h->stats.points_total += (uint64_t)nchan * (uint64_t)(2 * (m_end - p.m_skip));
+	h->stats.points_total += (uint64_t)nchan * (uint64_t)(2 * (m_end - p.m_skip)) * (uint64_t)(OS > 1 ? OS + 1 : 1);
 	h->pending = true;
 	return PHASEROT_OK;
 }
@@ -994,6 +1080,10 @@ phaserot_create (phaserot_t** out, const phaserot_cfg_t* cfg)
 	if (S < 1 || S > 1000) {
 		return PHASEROT_E_INVAL;
 	}
+	const int OS = cfg->oversample <= 1 ? 1 : cfg->oversample;
+	if (cfg->oversample < 0 || (OS != 1 && OS != 2 && OS != 4) || (OS > 1 && plugin)) {
+		return PHASEROT_E_INVAL;
+	}
 	if (L / 2 > kM) {
 		snprintf (g_last_error, sizeof (g_last_error), "FIR length %d needs %d half-taps; this build supports at most %d", L, L / 2, kM);
 		return PHASEROT_E_UNSUPPORTED;
@@ -1042,6 +1132,7 @@ phaserot_create (phaserot_t** out, const phaserot_cfg_t* cfg)
 	h->padf   = (h->Lh + 3) & ~3;
 	h->S      = S;
 	h->MS     = 180 * S;
+	h->OS     = OS;
 	h->plugin = plugin;
 	h->P      = P;
 	h->firlen = firlen;
@@ -1103,7 +1194,7 @@ phaserot_destroy (phaserot_t* h)
 	if (h->own_stream) cudaStreamSynchronize (h->own_stream);
 	if (h->copy_stream) cudaStreamSynchronize (h->copy_stream);
 	for (DevBuf* b : { &h->d_G, &h->d_G1, &h->d_scratch, &h->d_tw, &h->d_g, &h->d_plane, &h->d_out, &h->d_list, &h->d_stage[0], &h->d_stage[1], &h->d_io, &h->d_inter, &h->d_hist, &h->d_small,
-	                   &h->d_cs, &h->d_peaks, &h->d_ramp, &h->d_chancs }) {
+	                   &h->d_cs, &h->d_peaks, &h->d_ramp, &h->d_chancs, &h->d_tpH }) {
 		b->release ();
 	}
 	for (PinBuf* b : { &h->h_stage[0], &h->h_stage[1], &h->h_res, &h->h_io }) {

@@ -50,6 +50,7 @@ struct Options {
 	unsigned int blksiz     = 0;
 	const char*  in_path    = nullptr;
 	const char*  out_path   = nullptr;
+	int          oversample = 0; // --true-peak[=2|4]: opt-in long option of this backend, not in the reference
 };
 
 float
@@ -129,6 +130,7 @@ parse_options (int argc, char** argv)
 		{ "link-channels", no_argument, 0, 'l' },
 		{ "version", no_argument, 0, 'V' },
 		{ "verbose", no_argument, 0, 'v' },
+		{ "true-peak", optional_argument, 0, 1000 }, // new, long-only: the reference's options are unchanged
 		{ 0, 0, 0, 0 },
 	};
 	int c;
@@ -144,6 +146,12 @@ parse_options (int argc, char** argv)
 				printf ("Copyright (C) GPL 2021 Robin Gareus <robin@gareus.org>\n");
 				::exit (EXIT_SUCCESS);
 			case 'v': ++o.verbose; break;
+			case 1000:
+				o.oversample = optarg ? atoi (optarg) : 4;
+				if (o.oversample != 2 && o.oversample != 4) {
+					die ("Error: --true-peak takes an oversampling factor of 2 or 4.\n");
+				}
+				break;
 			default: die ("Error: unrecognized option. See --help for usage information.\n");
 		}
 	}
@@ -354,6 +362,7 @@ main (int argc, char** argv)
 	cfg.blksiz      = (int32_t)blksiz;
 	cfg.subsample   = kSubsample;
 	cfg.device      = -1;
+	cfg.oversample  = opt.oversample;
 	phaserot_t* pr  = nullptr;
 	check (phaserot_create (&pr, &cfg), "cannot initialise the CUDA backend");
 

@@ -47,6 +47,7 @@ def oracle():
         lib.pro_hilbert_fir.argtypes = [f32p, C.c_int64, f32p, C.c_int, f32p, C.c_int64]
         lib.pro_cli_analyze.argtypes = [f32p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f32p]
         lib.pro_cli_analyze_shard.argtypes = [f32p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f32p]
+        lib.pro_cli_analyze_tp_shard.argtypes = [f32p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, f32p]
         lib.pro_cli_apply.argtypes = [f32p, C.c_int64, C.c_int, C.c_int, C.c_int, i32p, C.c_int, f32p]
         lib.pro_cli_render_file.argtypes = [f32p, C.c_int64, C.c_int, C.c_int, C.c_int, i32p, f32p]
         lib.pro_cli_render_file.restype = C.c_int64
@@ -132,6 +133,25 @@ def oracle_analyze_shard(x, blksiz, hist, first, last, subsample=2, ang_start=0,
         assert hist.shape == (blksiz, c)
         hp = hist.ctypes.data
     oracle().pro_cli_analyze_shard(x, n, c, blksiz, subsample, hp, int(first), int(last), ang_start, ang_end, stride, only_chn, peaks)
+    return peaks
+
+
+def oracle_analyze_tp(x, blksiz, oversample=4, hist=None, first=True, last=True, subsample=2, ang_start=0, ang_end=None, stride=1,
+                      only_chn=-1, peaks=None):
+    """Oversampled true-peak analysis (this library's own definition, include/phaserot_cuda.h; not a reference feature)."""
+    x = _inter(x)
+    n, c = x.shape
+    ms = 180 * subsample
+    if ang_end is None:
+        ang_end = ms
+    if peaks is None:
+        peaks = np.zeros((c, ms), np.float32)
+    hp = None
+    if hist is not None:
+        hist = np.ascontiguousarray(hist, np.float32)
+        assert hist.shape == (blksiz, c)
+        hp = hist.ctypes.data
+    oracle().pro_cli_analyze_tp_shard(x, n, c, blksiz, subsample, oversample, hp, int(first), int(last), ang_start, ang_end, stride, only_chn, peaks)
     return peaks
 
 

@@ -240,6 +240,101 @@ def test_blksiz_32768_pruned_equals_brute_force_and_shards_combine():
     assert np.all(brute[:, 1:] > 0)
 
 
+# ---------------------------------------------------------------------------
+# oversampled true-peak sweep (new capability, not in the reference: parity is
+# against this repo's own CPU restatement of the definition in phaserot_cuda.h)
+# ---------------------------------------------------------------------------
+
+TP_CASES = {
+    "two_sine_2ch_L8192": (lambda: O.two_sine(48000, 2.0, 2), 8192),
+    "pink_mono_L4096": (lambda: O.pink_noise(90000, 5)[:, None], 4096),
+    "programme_2ch_L16384": (lambda: O.programme(96000, 1.0, 2), 16384),
+    "odd_len_3ch_L1024": (lambda: O.harmonic(48000, 0.5, 3)[:23999], 1024),
+    "one_frame_L2048": (lambda: np.array([[0.5, -0.25]], np.float32), 2048),
+    "harmonic_2ch_L32768": (lambda: O.harmonic(192000, 0.6, 2), 32768),
+}
+
+
+@pytest.mark.parametrize("name", sorted(TP_CASES))
+@pytest.mark.parametrize("os_", [2, 4])
+@pytest.mark.parametrize("flags", [0, capi.FLAG_NO_PRUNE])
+def test_true_peak_sweep_matches_oracle(name, os_, flags):
+    gen, L = TP_CASES[name]
+    x = gen()
+    po = O.oracle_analyze_tp(x, L, os_)
+    pd = O.oracle_analyze(x, L)
+    with capi.Phaserot(n_channels=x.shape[1], blksiz=L, flags=flags, oversample=os_) as h:
+        h.sweep(x)
+        pg = h.peaks()
+        kt = h.stats()
+    assert kt["kernel_launches"] > 0
+    assert rel(pg, po) <= PEAK_TOL
+    assert np.array_equal(pg[:, 0], po[:, 0])        # raw-input detector: same fp32 operations on both sides
+    assert np.all(pg >= pd * (1 - 1e-6))             # the digital peak is part of the true-peak detector
+    argmin_equal_unless_tied(pg, po)
+
+
+def test_true_peak_quirk_flag_ranges_and_streaming():
+    x = O.programme(48000, 1.5, 2)
+    L = 4096
+    # first-block rule switched off
+    with capi.Phaserot(n_channels=2, blksiz=L, oversample=4, flags=capi.FLAG_NO_FIRST_BLOCK_QUIRK) as h:
+        h.sweep(x)
+        fixed = h.peaks()
+    with capi.Phaserot(n_channels=2, blksiz=L, oversample=4) as h:
+        h.sweep(x)
+        quirk = h.peaks()
+        assert np.all(fixed >= quirk)
+        # a refine-style window on one channel
+        h.reset()
+        h.sweep(x, 30, 55, 1, 1)
+        win = h.peaks()
+        po = O.oracle_analyze_tp(x, L, 4, ang_start=30, ang_end=55, stride=1, only_chn=1)
+        assert rel(win[po > 0], po[po > 0]) <= PEAK_TOL and np.all(win[po == 0] == 0)
+        # block streaming (PhaseRotate::analyze drop-in) continues the interpolator across batches
+        h.reset()
+        nb = (x.shape[0] + L - 1) // L
+        xp = np.zeros((nb * L, 2), np.float32)
+        xp[:x.shape[0]] = x
+        for b in range(nb):
+            h.analyze(xp[b * L:(b + 1) * L], 0, 360, 1, -1, b == 0)
+            if b == 3:
+                h.sync()   # forces a batch boundary: the next batch continues from history
+        h.analyze(np.zeros((L, 2), np.float32), 0, 360, 1, -1, False)
+        assert rel(h.peaks(), quirk) <= 2e-6
+
+
+def test_true_peak_full_size_pruned_equals_brute_force_and_shards_combine():
+    """5 min stereo at 0.1 deg, 4x true-peak: pruning is exact, shards combine (to FFT rounding: the
+    shard with history computes the 11 interpolator samples before its start from that history)."""
+    import bench
+    x, frames = _device_programme(300.0)
+    with capi.Phaserot(n_channels=2, blksiz=bench.BLKSIZ, subsample=10, oversample=4) as h:
+        h.sweep_device(x.data_ptr(), frames)
+        pruned = h.peaks()
+        st = h.stats()
+        assert st["points_evaluated"] < 0.2 * st["points_total"]
+        al = h.shard_align()
+        half = (frames // 2) - ((frames // 2) % al)
+        h.reset()
+        h.sweep_shard_device(x.data_ptr(), half, None, True, False)
+        a = h.peaks()
+        hist = x[half - bench.BLKSIZ:half].cpu().numpy()
+        h.reset()
+        h.sweep_shard_device(x[half:].data_ptr(), frames - half, hist, False, True)
+        b = h.peaks()
+    with capi.Phaserot(n_channels=2, blksiz=bench.BLKSIZ, subsample=10, oversample=4, flags=capi.FLAG_NO_PRUNE) as h:
+        h.sweep_device(x.data_ptr(), frames)
+        brute = h.peaks()
+    with capi.Phaserot(n_channels=2, blksiz=bench.BLKSIZ, subsample=10) as h:
+        h.sweep_device(x.data_ptr(), frames)
+        digital = h.peaks()
+    assert np.array_equal(pruned, brute)
+    assert rel(np.maximum(a, b), brute) <= 2e-6
+    assert np.all(brute >= digital) and np.any(brute > digital)
+    assert np.all(brute <= digital * 1.5)
+
+
 def test_full_size_render_properties():
     """3 min stereo: angle 0 is a pure delay of blksiz/2; rendering is linear; +90 then the
     matching -90 rotation restores the (twice delayed) input away from DC/Nyquist effects."""
