@@ -234,6 +234,104 @@ def workload_config(args, ref=False):
 # GPU arm
 # ---------------------------------------------------------------------------
 
+def secondary_legs(torch, capi, dev, local, x, frames, hbm_peak):
+    """BASELINE.json's metric also names 'rotated Msamples/s': the CLI render (cli/phase-rotate.cc:950-1003,
+    config 4 style) and the plugin run() (src/phaserotate.c:774-852, config 2) measured on the same box,
+    plus the true-peak variant of the sweep (config 3).  Bounded to a few seconds."""
+    out = {}
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    # -- CLI render, device resident: 10 min stereo per call, fixed per-channel angles
+    rf = min(frames, 600 * SR)
+    rf -= rf % BLKSIZ
+    y = torch.empty(((rf // BLKSIZ + 1) * BLKSIZ, CHANNELS), device=dev, dtype=torch.float32)
+    with capi.Phaserot(mode=capi.MODE_CLI, n_channels=CHANNELS, blksiz=BLKSIZ, device=local) as hr:
+        hr.set_stream(torch.cuda.current_stream().cuda_stream)
+        for _ in range(2):
+            hr.render_device(x.data_ptr(), rf, [37, 181], 1, y.data_ptr())
+        torch.cuda.synchronize()
+        e0, e1 = ev(), ev()
+        e0.record()
+        n_r = 5
+        for _ in range(n_r):
+            hr.render_device(x.data_ptr(), rf, [37, 181], 1, y.data_ptr())
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n_r
+        hr.set_profiling(True)
+        hr.render_device(x.data_ptr(), rf, [37, 181], 1, y.data_ptr())
+        hr.sync()
+        kt = hr.kernel_times()
+        gbs = 8.0 * rf * CHANNELS / (ms * 1e-3) / 1e9
+        out["render"] = {"value": rf * CHANNELS / (ms * 1e-3) / 1e6, "unit": "rotated Msamples/s", "ms_per_call": ms,
+                         "workload": f"CLI render, stereo 48 kHz, {rf / SR:g} s per call, device resident, angles 18.5/90.5 deg",
+                         "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                                      "algorithmic_bytes_per_sample": 8},
+                         "kernels_ms": {k: round(v["ms"], 4) for k, v in kt.items() if v["launches"]}}
+    del y
+    # -- plugin run(): mono 48 kHz, angle port at 90 deg from the first call (ramp included), 1024-frame calls
+    rng = np.random.default_rng(42)
+    n_calls, blk = 2000, 1024
+    xin = (0.25 * rng.standard_normal(n_calls * blk)).astype(np.float32)
+    yout = np.zeros_like(xin)
+    ang = np.array([90.0], np.float32)
+    with capi.Phaserot(mode=capi.MODE_PLUGIN, n_channels=1, sample_rate=48000.0, device=local) as hp:
+        ins = (ctypes.c_void_p * 1)()
+        outs = (ctypes.c_void_p * 1)()
+        def run(lo, hi):
+            for k in range(lo, hi):
+                ins[0] = xin.ctypes.data + 4 * k * blk
+                outs[0] = yout.ctypes.data + 4 * k * blk
+                hp.process_raw(ins, outs, blk, ang)
+        run(0, 200)
+        t0 = time.perf_counter()
+        run(200, n_calls)
+        dt = time.perf_counter() - t0
+        out["plugin"] = {"value": (n_calls - 200) * blk / dt / 1e6, "unit": "rotated Msamples/s", "us_per_call": 1e6 * dt / (n_calls - 200),
+                         "workload": "LV2 run(): mono 48 kHz, 1024-frame calls, angle 90 deg, host buffers in and out (synchronous round trip per call)"}
+        # bulk: 10 min in one call (host buffers; H2D + D2H inside)
+        nb = 600 * SR
+        xb = (0.25 * rng.standard_normal(nb)).astype(np.float32)
+        yb = np.zeros_like(xb)
+        hp.reset()
+        ins[0], outs[0] = xb.ctypes.data, yb.ctypes.data
+        hp.process_raw(ins, outs, nb, ang)
+        hp.reset()
+        t0 = time.perf_counter()
+        hp.process_raw(ins, outs, nb, ang)
+        dt = time.perf_counter() - t0
+        out["plugin_bulk"] = {"value": nb / dt / 1e6, "unit": "rotated Msamples/s", "ms_per_call": 1e3 * dt,
+                              "workload": "LV2 run(): mono 48 kHz, one 600 s call, pageable host buffers in and out"}
+    # -- true-peak sweep (4x), same 1800-angle grid, 10 min stereo device resident
+    tf = min(frames, 600 * SR)
+    tf -= tf % (32768 - BLKSIZ)
+    with capi.Phaserot(mode=capi.MODE_CLI, n_channels=CHANNELS, blksiz=BLKSIZ, subsample=SUBSAMPLE, device=local, oversample=4) as ht:
+        ht.set_stream(torch.cuda.current_stream().cuda_stream)
+        for _ in range(2):
+            ht.reset()
+            ht.sweep_device(x.data_ptr(), tf)
+            ht.peaks()
+        e0, e1 = ev(), ev()
+        e0.record()
+        n_t = 3
+        for _ in range(n_t):
+            ht.reset()
+            ht.sweep_device(x.data_ptr(), tf)
+            ht.peaks()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n_t
+        ht.set_profiling(True)
+        ht.reset()
+        ht.sweep_device(x.data_ptr(), tf)
+        ht.peaks()
+        kt = ht.kernel_times()
+        out["true_peak"] = {"value": float(tf) * CHANNELS * 180 * SUBSAMPLE / (ms * 1e-3) / 1e9, "unit": "Gsample-angles/s", "ms_per_step": ms,
+                            "workload": f"4x oversampled true-peak sweep (new capability), stereo 48 kHz, {tf / SR:g} s, 1800 angles, device resident",
+                            "hbm_frac_algorithmic": 4.0 * tf * CHANNELS / (ms * 1e-3) / 1e9 / hbm_peak,
+                            "kernels_ms": {k: round(v["ms"], 4) for k, v in kt.items() if v["launches"]}}
+    return out
+
+
 def gpu_main(args):
     import torch
     import torch.distributed as dist
@@ -369,6 +467,11 @@ def gpu_main(args):
     step_ms = 1e3 * t_dev / args.steps
     kshare = {k: round(v["ms"], 4) for k, v in kt.items() if v["launches"]}
 
+    # ---- secondary legs (rank 0, N=1): the other two callers of the path.  Not part of `value`.
+    extra = {}
+    if world == 1 and not args.no_extra:
+        extra = secondary_legs(torch, capi, dev, local, x, frames, peak)
+
     line = None
     if rank == 0:
         cpu = None
@@ -404,6 +507,7 @@ def gpu_main(args):
             "pruning": {"enabled": not args.no_prune, "survivor_fraction": surv, "points_per_step_per_gpu": st["points_total"] // max(1, args.steps)},
             "cpu_baseline": cpu,
         }
+        line.update(extra)
     h.close()
     if world > 1:
         dist.barrier()
@@ -423,6 +527,7 @@ def main():
     ap.add_argument("--ref-seconds", type=float, default=240.0, help="bounded CPU sample for the reference arm")
     ap.add_argument("--no-prune", action="store_true", help="evaluate every sample at every angle")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the render / plugin / true-peak secondary legs")
     ap.add_argument("--wall", action="store_true", help="use max(wall, events) as the step time")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -44,7 +44,7 @@ class Stats(C.Structure):
 
 
 NKERNELS = 7
-KERNEL_NAMES = ["fftconv_filter", "sweep", "deinterleave", "fftconv_render", "fir_direct", "other", "truepeak_filter"]
+KERNEL_NAMES = ["fftconv_filter", "sweep", "deinterleave", "fftconv_render", "fir_stream", "other", "truepeak_filter"]
 
 
 class KTimes(C.Structure):

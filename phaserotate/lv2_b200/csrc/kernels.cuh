@@ -10,7 +10,8 @@
 // K3 sweep_kernel          every angle over a survivor list, angles in lanes,
 //                          running max in registers, one atomicMax per angle/CTA
 //    threshold_kernel      min over angles of the running peaks -> next filter radius
-//    fir_direct_kernel     small-call plugin path: direct-form FIR + rotate
+//    fir_stream_kernel     small-call plugin path: direct-form FIR + rotate, history in a device ring
+//    truepeak_kernel       oversampled true-peak front end of the sweep
 //
 // Data layout.  A channel's samples x[0..F) are viewed as complex numbers
 // z[n] = x[2n] + i x[2n+1] ("plane", float2, with a zero front pad).  The
@@ -673,59 +674,71 @@ __global__ void threshold_kernel (const unsigned* __restrict__ peaks, int peaks_
 	}
 }
 
-// ---------------------------------------------------------------------------
-// Small-call plugin path: direct-form FIR + rotation for n outputs per channel.
-// hist[c] is a linear window of the input stream ending at the newest sample:
-// hist[c][hlen - 1] = x[t_end - 1].  Output u in [u0, u0 + n):
-//   Y[u] = ca_u * x[u - firlat] + sa_u * sum_j g[j] x[u - 1 - 2j]
-// (ca, sa) for output i: pre[c][i] for i < fc.rlen[c], fc.cs[c] after that.
-// ---------------------------------------------------------------------------
+// (ca, sa) of the plugin's small-call path: output i of channel c uses
+// pre[c][i] for i < rlen[c] (angle ramp, src:673-709) and cs[c] after that.
 struct FirCoef {
 	float2 cs[2];
 	int    rlen[2];
 };
-__global__ void __launch_bounds__ (128) fir_direct_kernel (const float* __restrict__ hist, int hist_stride, int hlen,
-                                                            long long t_end, long long u0, int n,
-                                                            const float* __restrict__ g, int nodd, int firlat,
-                                                            const float2* __restrict__ pre, int pre_stride, FirCoef fc,
-                                                            float* __restrict__ out, int out_stride)
+// ---------------------------------------------------------------------------
+// Small-call plugin path, streaming form: the input history of every channel
+// lives in a device ring (kRing floats, index = stream position & (kRing - 1)),
+// a run() call only ships its n new samples (mapped pinned memory, read once)
+// and gets n outputs back (written straight to mapped pinned memory).  One
+// launch per run().  CTA = 32 outputs x 4 tap quarters; output u in
+// [u0, u0 + n), u0 = t0 - parsiz:
+//   Y[u] = ca_u * x[u - firlat] + sa_u * sum_j g[j] x[u - 1 - 2j]      (src:629-717)
+// Every CTA also appends its 32 new samples to the ring; they are read by later
+// calls only (positions >= t0 are never read from the ring in this launch, and
+// n + firlen + parsiz <= kRing keeps them clear of the history being read).
+// ---------------------------------------------------------------------------
+constexpr int kRing      = 32768;
+constexpr int kStreamOut = 32;
+
+__global__ void __launch_bounds__ (128) fir_stream_kernel (float* __restrict__ ring, const float* __restrict__ xin, int xin_stride, int n,
+                                                            long long t0, int parsiz, const float* __restrict__ g, int nodd, int firlat,
+                                                            const float2* __restrict__ pre, int pre_stride, FirCoef fc, float* __restrict__ yout)
 {
-	extern __shared__ float sh[]; // g[nodd] then x window
-	const int c   = blockIdx.y;
-	const int o0  = blockIdx.x * blockDim.x; // first output of this CTA (relative)
-	const int nb  = min ((int)blockDim.x, n - o0);
-	if (nb <= 0) return;
-	float* sg = sh;
-	float* sx = sh + nodd;
-	for (int j = threadIdx.x; j < nodd; j += blockDim.x) sg[j] = g[j];
-	// window: x[u_lo - 2 nodd + 1 .. u_hi], u_lo = u0 + o0
-	const long long u_lo = u0 + o0;
-	const int       wlen = 2 * nodd + nb;
-	const long long w0   = u_lo - 2 * nodd; // stream index of sx[0]
-	const float*    hc   = hist + (long long)c * hist_stride;
-	const long long h0   = t_end - hlen;     // stream index of hist[0]
-	for (int i = threadIdx.x; i < wlen; i += blockDim.x) {
+	extern __shared__ float sh[]; // g[nodd] | window[2 nodd + 32] | partial[4][32]
+	const int c  = blockIdx.y;
+	const int o0 = blockIdx.x * kStreamOut;
+	const int nb = min (kStreamOut, n - o0);
+	float*    sg = sh;
+	float*    sx = sh + nodd;
+	float*    sp = sx + 2 * nodd + kStreamOut;
+	float*       rc = ring + (long long)c * kRing;
+	const float* xc = xin + (long long)c * xin_stride;
+	for (int j = threadIdx.x; j < nodd; j += blockDim.x) sg[j] = __ldg (g + j);
+	// window: stream positions w0 .. w0 + 2 nodd + nb - 1, w0 = u_lo - 2 nodd, u_lo = t0 - parsiz + o0
+	const long long w0 = t0 - parsiz + o0 - 2 * nodd;
+	for (int i = threadIdx.x; i < 2 * nodd + nb; i += blockDim.x) {
 		const long long t = w0 + i;
-		sx[i]             = (t >= h0 && t < t_end && t >= 0) ? hc[t - h0] : 0.f;
+		sx[i]             = t < 0 ? 0.f : (t < t0 ? rc[t & (kRing - 1)] : xc[t - t0]);
+	}
+	if ((int)threadIdx.x < nb) rc[(t0 + o0 + threadIdx.x) & (kRing - 1)] = xc[o0 + threadIdx.x];
+	__syncthreads ();
+	const int o = threadIdx.x & 31, q = threadIdx.x >> 5;
+	{
+		// x[u - 1 - 2j] = sx[2 nodd + o - 1 - 2j]
+		const int    nq = nodd >> 2; // nodd is a multiple of 4 (1536 / 2048 / 4096)
+		const float* xp = sx + 2 * nodd + o - 1 - 2 * q * nq;
+		const float* gp = sg + q * nq;
+		float        a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+		for (int j = 0; j < nq; j += 4) {
+			a0 = fmaf (gp[j], xp[-2 * j], a0);
+			a1 = fmaf (gp[j + 1], xp[-2 * j - 2], a1);
+			a2 = fmaf (gp[j + 2], xp[-2 * j - 4], a2);
+			a3 = fmaf (gp[j + 3], xp[-2 * j - 6], a3);
+		}
+		sp[q * 32 + o] = (a0 + a1) + (a2 + a3);
 	}
 	__syncthreads ();
-	const int i = threadIdx.x;
-	if (i < nb) {
-		// x[u - 1 - 2j] = sx[(u - w0) - 1 - 2j], u - w0 = 2 nodd + i
-		const float* xp  = sx + 2 * nodd + i - 1;
-		float        a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-		int          j  = 0;
-		for (; j + 3 < nodd; j += 4) {
-			a0 = fmaf (sg[j], xp[-2 * j], a0);
-			a1 = fmaf (sg[j + 1], xp[-2 * j - 2], a1);
-			a2 = fmaf (sg[j + 2], xp[-2 * j - 4], a2);
-			a3 = fmaf (sg[j + 3], xp[-2 * j - 6], a3);
-		}
-		for (; j < nodd; ++j) a0 = fmaf (sg[j], xp[-2 * j], a0);
-		const float  h  = (a0 + a1) + (a2 + a3);
-		const float  xd = sx[2 * nodd + i - firlat];
-		const float2 cs = (o0 + i) < fc.rlen[c] ? pre[(long long)c * pre_stride + o0 + i] : fc.cs[c];
-		out[(long long)c * out_stride + o0 + i] = __fadd_rn (__fmul_rn (cs.x, xd), __fmul_rn (cs.y, h));
+	if (q == 0 && o < nb) {
+		const float  hv = (sp[o] + sp[32 + o]) + (sp[64 + o] + sp[96 + o]);
+		const float  xd = sx[2 * nodd + o - firlat];
+		const float2 cs = (o0 + o) < fc.rlen[c] ? pre[(long long)c * pre_stride + o0 + o] : fc.cs[c];
+		yout[(long long)c * n + o0 + o] = __fadd_rn (__fmul_rn (cs.x, xd), __fmul_rn (cs.y, hv));
 	}
 }
 

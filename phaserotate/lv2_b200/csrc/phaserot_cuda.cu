@@ -227,6 +227,8 @@ struct phaserot {
 	std::vector<PluginChan> pch;
 	std::vector<float>      ptail; // [C][firlen + P] newest input last
 	uint64_t                ppos = 0;
+	DevBuf                  d_ring;             // [C][kRing] input history of the small-call path
+	bool                    ring_valid = false; // false: re-seed the ring from ptail before the next small call
 
 	phaserot_stats_t stats {};
 
@@ -1194,7 +1196,7 @@ phaserot_destroy (phaserot_t* h)
 	if (h->own_stream) cudaStreamSynchronize (h->own_stream);
 	if (h->copy_stream) cudaStreamSynchronize (h->copy_stream);
 	for (DevBuf* b : { &h->d_G, &h->d_G1, &h->d_scratch, &h->d_tw, &h->d_g, &h->d_plane, &h->d_out, &h->d_list, &h->d_stage[0], &h->d_stage[1], &h->d_io, &h->d_inter, &h->d_hist, &h->d_small,
-	                   &h->d_cs, &h->d_peaks, &h->d_ramp, &h->d_chancs, &h->d_tpH }) {
+	                   &h->d_cs, &h->d_peaks, &h->d_ramp, &h->d_chancs, &h->d_tpH, &h->d_ring }) {
 		b->release ();
 	}
 	for (PinBuf* b : { &h->h_stage[0], &h->h_stage[1], &h->h_res, &h->h_io }) {
@@ -1241,7 +1243,8 @@ phaserot_reset (phaserot_t* h)
 	if (h->plugin) {
 		// activate() clears buffers but keeps the angle state (src:169-177, 511-520)
 		std::fill (h->ptail.begin (), h->ptail.end (), 0.f);
-		h->ppos = 0;
+		h->ppos       = 0;
+		h->ring_valid = false;
 		for (auto& ch : h->pch) {
 			ch.last_is_ramp = false;
 			ch.last_const   = make_float2 (ch.ca, ch.sa);
@@ -1629,13 +1632,32 @@ phaserot_process (phaserot_t* h, const float* const* in, float* const* out, uint
 	h->ppos += n;
 
 	if (small && h->h_io.d) {
-		// small call: direct-form FIR straight out of mapped pinned memory
+		// small call: one launch.  The history stays in a device ring; the kernel
+		// reads the n new samples from mapped pinned memory and writes the n
+		// outputs back to it.
 		const int    nodd = h->Lh;
-		const size_t smem = sizeof (float) * (3 * (size_t)nodd + 128);
+		const size_t smem = sizeof (float) * (3 * (size_t)nodd + kStreamOut + 128);
 		static bool  attr = false;
 		if (!attr) {
-			CK (cudaFuncSetAttribute (fir_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+			CK (cudaFuncSetAttribute (fir_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
 			attr = true;
+		}
+		rc = h->d_ring.ensure (sizeof (float) * (size_t)kRing * C);
+		if (rc) return rc;
+		if (!h->ring_valid) {
+			// (re-)seed: W[c][0 .. keep) are stream positions [t0 - keep, t0)
+			for (int c = 0; c < C; ++c) {
+				float*       r   = (float*)h->d_ring.p + (size_t)c * kRing;
+				const float* w   = W + wstride * c;
+				uint64_t     i0  = t0 < keep ? keep - t0 : 0; // positions before the stream start are never read
+				while (i0 < keep) {
+					const uint64_t pos = (t0 - keep + i0) & (kRing - 1);
+					const uint64_t cnt = std::min<uint64_t> (keep - i0, kRing - pos);
+					CK (cudaMemcpyAsync (r + pos, w + i0, sizeof (float) * cnt, cudaMemcpyHostToDevice, h->stream));
+					i0 += cnt;
+				}
+			}
+			h->ring_valid = true;
 		}
 		const char*   dbase = (const char*)h->h_io.d;
 		const float*  dW    = (const float*)dbase;
@@ -1646,20 +1668,23 @@ phaserot_process (phaserot_t* h, const float* const* in, float* const* out, uint
 			fc.cs[c]   = chan_cs[c < C ? c : 0];
 			fc.rlen[c] = ramp_len[c < C ? c : 0];
 		}
-		const dim3 grid ((n + 127) / 128, (unsigned)C);
-		ProfScope  ps (h, 4);
-		fir_direct_kernel<<<grid, 128, smem, h->stream>>> (dW, (int)wstride, (int)wlen, (long long)wlen, (long long)firlen, (int)n,
-		                                                    (const float*)h->d_g.p, nodd, (int)h->firlat, dpre, (int)pre_cap, fc, dy, (int)n);
+		const dim3 grid ((n + kStreamOut - 1) / kStreamOut, (unsigned)C);
+		{
+			ProfScope ps (h, 4);
+			fir_stream_kernel<<<grid, 128, smem, h->stream>>> ((float*)h->d_ring.p, dW + keep, (int)wstride, (int)n, (long long)t0, (int)P,
+			                                                    (const float*)h->d_g.p, nodd, (int)h->firlat, dpre, (int)pre_cap, fc, dy);
+		}
 		CK (cudaGetLastError ());
 		++h->stats.kernel_launches;
 		CK (cudaStreamSynchronize (h->stream));
 		for (int c = 0; c < C; ++c) {
 			memcpy (out[c], yout + (size_t)c * n, sizeof (float) * n);
 		}
-		h->stats.h2d_bytes += sizeof (float) * wlen * C;
+		h->stats.h2d_bytes += sizeof (float) * (size_t)n * C;
 		h->stats.d2h_bytes += sizeof (float) * (size_t)n * C;
 		return PHASEROT_OK;
 	}
+	h->ring_valid = false; // the bulk path does not maintain the ring
 
 	// bulk call: FFT convolution over W (planar already: one "channel-major" upload)
 	{
