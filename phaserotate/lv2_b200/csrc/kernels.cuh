@@ -33,7 +33,9 @@
 namespace prk {
 
 constexpr int kXchFloats = 16 * 32;                                   // Im of lane 31's outputs, per warp
-constexpr int kSmemBytes = kM * (int)sizeof (float2) + (kXchFloats + 4 + kConvThreads) * (int)sizeof (float); // + TMEM base address slot + thread ids
+constexpr int kRedThr    = 24;                                       // slot of the launch's squared filter radius
+constexpr int kRedFloats = 32;                                       // block reductions (filter radius, bootstrap gate)
+constexpr int kSmemBytes = kM * (int)sizeof (float2) + (kXchFloats + 4 + kConvThreads + kRedFloats) * (int)sizeof (float); // + TMEM base address slot + thread ids
 
 enum { EPI_POINTS = 0, EPI_RENDER = 1, EPI_HILBERT = 2 };
 
@@ -68,8 +70,18 @@ struct ConvParams {
 	float2*       list;         // [n_chan][list_stride]
 	long long     list_stride;
 	unsigned*     count;        // [n_chan]
-	const float*  thr2;         // [n_chan] squared filter radius
+	const float*  thr2;         // [n_chan] squared filter radius (thr_mode < 0: written by threshold_kernel)
 	unsigned*     rawpeak;      // [n_chan] bits of max |x|
+	// EPI_POINTS, thr_mode >= 0: the filter radius is derived inside the kernel from the
+	// running peaks (what threshold_kernel computes), 0 keep every point, 1 prune, 2 drop every point
+	int             thr_mode;
+	const unsigned* peaks;      // [n_chan][peaks_stride] float bits of the running per-angle maxima
+	int             peaks_stride, A;
+	unsigned*       count_reset; // [n_chan] counters of the previous launch's list (already swept): zeroed here
+	// bootstrap launch: additionally gate on boot_beta * (largest squared radius seen so far
+	// in this launch, r2max[c]) - only the strongest points of the sampled segments are kept
+	float           boot_beta;
+	unsigned*       r2max;      // [n_chan] float bits
 	// EPI_RENDER / EPI_HILBERT
 	float2*       out;          // [n_chan][out_stride], element m
 	long long     out_stride;
@@ -239,18 +251,83 @@ __device__ __forceinline__ void load_direct (float2 (&zd)[4], const bool (&ok)[4
 	}
 }
 
+// Bounds-checked walk over the outputs of a segment (segments at the stream edges,
+// delays that are not a multiple of the stash stride, and the bootstrap pre-pass):
+// f (p0, p1, in, ok, zd) per output pair i = tid + 512 k, where p0 / p1 are the
+// analytic pairs of samples 2m and 2m + 1, `ok` = the pair exists, `in` = it is
+// also examined (first-block rule), zd = the raw direct-branch inputs.
+template <class Loader, class F>
+__device__ __forceinline__ void walk_pairs_checked (const float2 (&w)[32], const float* xch, uint32_t tb, const ConvParams& p, int tid, int lane, const EpiCtx& cx, const Loader& ld, F&& f)
+{
+	const int dl    = p.dl;
+	const int warp  = tid >> 5;
+	const int xbase = warp ? (warp - 1) * 32 : 15 * 32 - 1;
+#pragma unroll 1
+	for (int kb = 0; kb < 32; kb += 4) {
+		if (512 * (kb + 4) <= p.Lh) continue; // whole block in the overlap region (uniform)
+		float2 zd[4];
+		bool   ok[4];
+#pragma unroll
+		for (int kk = 0; kk < 4; ++kk) {
+			const int i = tid + 512 * (kb + kk);
+			ok[kk]      = i >= p.Lh && i < cx.i_hi;
+		}
+		load_direct (zd, ok, tid, kb, dl, tb, ld);
+#pragma unroll
+		for (int kk = 0; kk < 4; ++kk) {
+			const int k  = kb + kk;
+			const int i  = tid + 512 * k;
+			float     wy = w[0].y, wx = w[0].x;
+#pragma unroll
+			for (int kq = 1; kq < 32; ++kq) { // rare path: select instead of unrolling the block loop
+				if (kq == k) {
+					wy = w[kq].y;
+					wx = w[kq].x;
+				}
+			}
+			float pv = __shfl_up_sync (0xffffffffu, wy, 1);
+			if (lane == 0) pv = xch[xbase + k];
+			const float2 z = i < cx.i_zero ? make_float2 (0.f, 0.f) : zd[kk];
+			f (make_float2 (z.x, pv), make_float2 (z.y, wx), ok[kk] && i >= cx.i_skip, ok[kk], zd[kk]);
+		}
+	}
+}
+
 template <int EPI, class Loader>
-__device__ __forceinline__ void epilogue (const float2 (&w)[32], const float* xch, uint32_t tb, const ConvParams& p, int tid, int lane, EpiCtx& cx, const Loader& ld)
+__device__ __forceinline__ void epilogue (const float2 (&w)[32], float* xch, uint32_t tb, const ConvParams& p, int tid, int lane, EpiCtx& cx, const Loader& ld)
 {
 	const int dl    = p.dl;
 	const int warp  = tid >> 5;
 	const int xbase = warp ? (warp - 1) * 32 : 15 * 32 - 1;
 	if (EPI == EPI_POINTS) {
-		const float    thr2   = p.thr2[cx.c];
+		float          thr2   = xch[kXchFloats + 4 + kConvThreads + kRedThr]; // parked in shared memory by the kernel prologue
 		float2*        lst    = p.list + (long long)cx.c * p.list_stride;
 		unsigned*      cnt    = p.count + cx.c;
 		const unsigned lt     = lanemask_lt ();
 		float          rawmax = cx.rawmax;
+		if (p.boot_beta > 0.f) {
+			// Bootstrap launch (uniform branch): largest squared radius of this segment,
+			// merged with what the other CTAs of the launch have published so far; only
+			// points within boot_beta of it are kept.  Any subset is valid here - the
+			// bootstrap only has to raise the running peaks, the contiguous passes
+			// visit every segment again.
+			float r2m = 0.f;
+			walk_pairs_checked (w, xch, tb, p, tid, lane, cx, ld, [&] (float2 p0, float2 p1, bool in, bool, float2) {
+				if (in) r2m = fmaxf (r2m, fmaxf (fmaf (p0.x, p0.x, p0.y * p0.y), fmaf (p1.x, p1.x, p1.y * p1.y)));
+			});
+			for (int o = 16; o; o >>= 1) r2m = fmaxf (r2m, __shfl_xor_sync (0xffffffffu, r2m, o));
+			float* red = xch + kXchFloats + 4 + kConvThreads;
+			if (lane == 0) red[warp] = r2m;
+			__syncthreads ();
+			if (tid == 0) {
+				float m = red[0];
+				for (int i = 1; i < kConvThreads / 32; ++i) m = fmaxf (m, red[i]);
+				const unsigned old = atomicMax (p.r2max + cx.c, __float_as_uint (m));
+				red[kConvThreads / 32] = fmaxf (m, __uint_as_float (old));
+			}
+			__syncthreads ();
+			thr2 = fmaxf (thr2, p.boot_beta * red[kConvThreads / 32]);
+		}
 		// interior segment whose valid region starts on a block of four strides:
 		// no bounds logic, the direct branch comes from the TMEM stash
 		const bool interior = cx.i_hi == kM && cx.i_skip == p.Lh && cx.i_zero == p.Lh && stash_usable (dl);
@@ -281,40 +358,12 @@ __device__ __forceinline__ void epilogue (const float2 (&w)[32], const float* xc
 				}
 			}
 		} else {
-#pragma unroll 1
-			for (int kb = 0; kb < 32; kb += 4) {
-				if (512 * (kb + 4) <= p.Lh) continue; // whole block in the overlap region (uniform)
-				float2 zd[4];
-				bool   ok[4];
-#pragma unroll
-				for (int kk = 0; kk < 4; ++kk) {
-					const int i = tid + 512 * (kb + kk);
-					ok[kk]      = i >= p.Lh && i < cx.i_hi;
-				}
-				load_direct (zd, ok, tid, kb, dl, tb, ld);
-#pragma unroll
-				for (int kk = 0; kk < 4; ++kk) {
-					const int k  = kb + kk;
-					const int i  = tid + 512 * k;
-					float     wy = w[0].y, wx = w[0].x;
-#pragma unroll
-					for (int kq = 1; kq < 32; ++kq) { // rare path: select instead of unrolling the block loop
-						if (kq == k) {
-							wy = w[kq].y;
-							wx = w[kq].x;
-						}
-					}
-					float pv = __shfl_up_sync (0xffffffffu, wy, 1);
-					if (lane == 0) pv = xch[xbase + k];
-					if (ok[kk]) rawmax = fmaxf (rawmax, fmaxf (fabsf (zd[kk].x), fabsf (zd[kk].y)));
-					const float2 z  = i < cx.i_zero ? make_float2 (0.f, 0.f) : zd[kk];
-					const float2 p0 = make_float2 (z.x, pv), p1 = make_float2 (z.y, wx);
-					const bool   in = ok[kk] && i >= cx.i_skip;
-					const bool   k0 = in && fmaf (p0.x, p0.x, p0.y * p0.y) >= thr2;
-					const bool   k1 = in && fmaf (p1.x, p1.x, p1.y * p1.y) >= thr2;
-					if (__any_sync (0xffffffffu, k0 || k1)) append_points (lst, cnt, k0, p0, k1, p1, lt, lane);
-				}
-			}
+			walk_pairs_checked (w, xch, tb, p, tid, lane, cx, ld, [&] (float2 p0, float2 p1, bool in, bool ok, float2 zd) {
+				if (ok) rawmax = fmaxf (rawmax, fmaxf (fabsf (zd.x), fabsf (zd.y)));
+				const bool k0 = in && fmaf (p0.x, p0.x, p0.y * p0.y) >= thr2;
+				const bool k1 = in && fmaf (p1.x, p1.x, p1.y * p1.y) >= thr2;
+				if (__any_sync (0xffffffffu, k0 || k1)) append_points (lst, cnt, k0, p0, k1, p1, lt, lane);
+			});
 		}
 		cx.rawmax = rawmax;
 	} else {
@@ -438,6 +487,36 @@ __global__ void __launch_bounds__ (kConvThreads, 1) fftconv_kernel (const ConvPa
 	const uint32_t tmem = tmem_alloc_all (reinterpret_cast<uint32_t*> (xch + kXchFloats), tid);
 	const uint32_t tb   = tmem_thread_base (tmem, tid);
 	const int lane = tid & 31;
+	EpiCtx cx;
+	cx.rawmax = 0.f;
+	if (EPI == EPI_POINTS) {
+		// filter radius of this launch: thr2 = (min_a peaks[c][a])^2 (1 - 1e-5), see
+		// threshold_kernel; parked in shared memory for the epilogues
+		const int cc  = p.chan0 + (int)blockIdx.x % p.nchan;
+		float*    red = xch + kXchFloats + 4 + kConvThreads;
+		float     t2  = 0.f;
+		if (p.thr_mode < 0) {
+			t2 = p.thr2[cc];
+		} else if (p.thr_mode == 2) {
+			t2 = __int_as_float (0x7f800000);
+		} else if (p.thr_mode == 1) {
+			float m = __int_as_float (0x7f800000);
+			for (int a = tid; a < p.A; a += kConvThreads) m = fminf (m, __uint_as_float (p.peaks[(long long)cc * p.peaks_stride + a]));
+			for (int o = 16; o; o >>= 1) m = fminf (m, __shfl_xor_sync (0xffffffffu, m, o));
+			if (lane == 0) red[tid >> 5] = m;
+			__syncthreads ();
+			m = red[0];
+			for (int i = 1; i < kConvThreads / 32; ++i) m = fminf (m, red[i]);
+			t2 = (m * m) * 0.99999f;
+		}
+		if (tid == 0) {
+			red[kRedThr] = t2;
+			if (p.count_reset) {
+				for (int i = 0; i < p.nchan; ++i) p.count_reset[p.chan0 + i] = 0; // every CTA writes the same zeros
+			}
+		}
+		// visible to every thread after the barriers of the first segment
+	}
 	{
 		// this thread's share of the filter spectrum -> TMEM (rows tid and tid + 512 of MID)
 		const float4* G4 = reinterpret_cast<const float4*> (p.G);
@@ -451,9 +530,6 @@ __global__ void __launch_bounds__ (kConvThreads, 1) fftconv_kernel (const ConvPa
 		}
 		tmem_wait_st ();
 	}
-
-	EpiCtx cx;
-	cx.rawmax = 0.f;
 
 	// CTA b owns channel b % nchan and, among the CTAs of that channel, a
 	// contiguous run of the launch's segments: consecutive segments share Lh

@@ -261,8 +261,8 @@ struct DevGuard {
 	}
 };
 
-// d_small: count[64] | thr2[64] | raw[64] | ramp_len[64] | stats[2 x u64]
-constexpr size_t kSmallBytes = 4 * 64 * sizeof (int) + 2 * sizeof (unsigned long long);
+// d_small: count[64] | thr2[64] | raw[64] | ramp_len[64] | stats[2 x u64] | count of odd launches[64] | r2max[64]
+constexpr size_t kSmallBytes = 6 * 64 * sizeof (int) + 2 * sizeof (unsigned long long);
 struct ProfScope {
 	phaserot* h;
 	size_t    slot = (size_t)-1;
@@ -308,6 +308,8 @@ float*              d_thr2 (phaserot* h) { return (float*)h->d_small.p + 64; }
 unsigned*           d_raw (phaserot* h) { return (unsigned*)h->d_small.p + 128; }
 int*                d_ramplen (phaserot* h) { return (int*)h->d_small.p + 192; }
 unsigned long long* d_stats (phaserot* h) { return (unsigned long long*)((char*)h->d_small.p + 4 * 64 * sizeof (int)); }
+unsigned*           d_count_odd (phaserot* h) { return (unsigned*)((char*)h->d_small.p + 4 * 64 * sizeof (int) + 2 * sizeof (unsigned long long)); }
+unsigned*           d_r2max (phaserot* h) { return d_count_odd (h) + 64; }
 
 int
 upload_tables (phaserot* h)
@@ -445,6 +447,9 @@ init_front_pad (phaserot* h, const float* hist_frames)
 	return PHASEROT_OK;
 }
 
+// bootstrap gate of the digital sweep: keep points with r^2 >= kBootBeta * (largest r^2 seen), i.e. r >= 0.8 r_max
+constexpr float kBootBeta = 0.64f;
+
 struct SweepCfg {
 	int nt, R, gy;
 };
@@ -471,7 +476,7 @@ pick_sweep_cfg (int A)
 }
 
 int
-launch_sweep (phaserot* h, int A, int c0, int nchan)
+launch_sweep (phaserot* h, int A, int c0, int nchan, const unsigned* count)
 {
 	const SweepCfg sc = pick_sweep_cfg (A);
 	int gx = (h->n_sm * 8) / std::max (1, sc.gy * nchan);
@@ -483,10 +488,10 @@ launch_sweep (phaserot* h, int A, int c0, int nchan)
 	unsigned long long* ne  = d_stats (h) + 1;
 	ProfScope           ps (h, 1);
 	switch (sc.R) {
-		case 1: sweep_kernel<1><<<grid, sc.nt, 0, h->stream>>> (lst, h->list_stride, d_count (h), c0, cs, A, pk, h->pend_A, ne); break;
-		case 2: sweep_kernel<2><<<grid, sc.nt, 0, h->stream>>> (lst, h->list_stride, d_count (h), c0, cs, A, pk, h->pend_A, ne); break;
-		case 4: sweep_kernel<4><<<grid, sc.nt, 0, h->stream>>> (lst, h->list_stride, d_count (h), c0, cs, A, pk, h->pend_A, ne); break;
-		default: sweep_kernel<8><<<grid, sc.nt, 0, h->stream>>> (lst, h->list_stride, d_count (h), c0, cs, A, pk, h->pend_A, ne); break;
+		case 1: sweep_kernel<1><<<grid, sc.nt, 0, h->stream>>> (lst, h->list_stride, count, c0, cs, A, pk, h->pend_A, ne); break;
+		case 2: sweep_kernel<2><<<grid, sc.nt, 0, h->stream>>> (lst, h->list_stride, count, c0, cs, A, pk, h->pend_A, ne); break;
+		case 4: sweep_kernel<4><<<grid, sc.nt, 0, h->stream>>> (lst, h->list_stride, count, c0, cs, A, pk, h->pend_A, ne); break;
+		default: sweep_kernel<8><<<grid, sc.nt, 0, h->stream>>> (lst, h->list_stride, count, c0, cs, A, pk, h->pend_A, ne); break;
 	}
 	CK (cudaGetLastError ());
 	++h->stats.kernel_launches;
@@ -653,9 +658,24 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 	p.thr2        = d_thr2 (h);
 	p.rawpeak     = d_raw (h);
 	const int thr_mode = A == 0 ? 2 : (h->cfg.flags & PHASEROT_FLAG_NO_PRUNE) ? 0 : 1;
-	threshold_kernel<<<nchan, 32, 0, h->stream>>> ((const unsigned*)h->d_peaks.p, A, A, c0, d_thr2 (h), d_count (h), 1, A == 0 ? 2 : 0);
-	CK (cudaGetLastError ());
-	++h->stats.kernel_launches;
+	if (OS > 1) {
+		// true-peak: the radius filter sits in truepeak_kernel and reads thr2 from memory
+		threshold_kernel<<<nchan, 32, 0, h->stream>>> ((const unsigned*)h->d_peaks.p, A, A, c0, d_thr2 (h), d_count (h), 1, A == 0 ? 2 : 0);
+		CK (cudaGetLastError ());
+		++h->stats.kernel_launches;
+		p.thr_mode = -1;
+	} else {
+		// digital peak: the FFT kernel derives the radius from the running peaks in its
+		// prologue and zeroes the counters of the list the previous sweep has consumed
+		// (two counter sets, alternating by launch), so a steady-state round is two
+		// launches: fftconv_kernel, sweep_kernel
+		p.thr_mode     = thr_mode;
+		p.peaks        = (const unsigned*)h->d_peaks.p;
+		p.peaks_stride = A;
+		p.A            = A;
+		p.r2max        = d_r2max (h);
+	}
+	int parity = 0;
 
 	long long       frames_ready = 0; // frames of `inter` that are valid on the device
 	long long       seg_done     = 0;
@@ -697,7 +717,7 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 	};
 
 	// one conv launch + sweep of its survivors + new filter radius
-	auto run_launch = [&] (long long s0, long long stride, long long n) -> int {
+	auto run_launch = [&] (long long s0, long long stride, long long n, bool boot = false) -> int {
 		p.seg0       = s0;
 		p.seg_stride = stride;
 		p.nseg       = n;
@@ -720,11 +740,20 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 				if (r) return r;
 			}
 		} else {
+			p.count       = parity ? d_count_odd (h) : d_count (h);
+			p.count_reset = parity ? d_count (h) : d_count_odd (h);
+			p.boot_beta   = boot ? kBootBeta : 0.f;
 			r = launch_conv<EPI_POINTS, SRC_INTER> (h, p);
 			if (r) return r;
+			if (A > 0) {
+				r = launch_sweep (h, A, c0, nchan, p.count);
+				if (r) return r;
+			}
+			parity ^= 1;
+			return PHASEROT_OK;
 		}
 		if (A > 0) {
-			r = launch_sweep (h, A, c0, nchan);
+			r = launch_sweep (h, A, c0, nchan, d_count (h));
 			if (r) return r;
 		}
 		{
@@ -756,13 +785,22 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 		const long long seg_ready = final ? nseg : std::min (nseg, frames_ready / (2 * (long long)h->V));
 		if (!booted && seg_ready >= 2 * wave) {
 			// Bootstrap the filter radius from a sparse sample of the segments
-			// available so far: a handful first (everything survives, radius 0),
-			// then one wave spread over the range.  The main passes below visit
-			// these segments again, which is harmless for a running maximum.
-			const long long n1 = std::max<long long> (1, 8 / nchan);
-			int r = run_launch (seg_ready / (2 * n1), seg_ready / n1, n1);
-			if (r) return r;
-			r = run_launch (0, seg_ready / wave, wave);
+			// available so far.  Digital peak: one wave spread over the range, of
+			// which only the strongest points (squared radius within kBootBeta of the
+			// largest one the launch has seen) are swept - a few hundred well-spread
+			// strong points already put every angle's running peak close to its
+			// final value.  True-peak: a handful of segments with everything kept,
+			// then one wave.  The main passes below visit these segments again,
+			// which is harmless for a running maximum.
+			int r;
+			if (OS > 1) {
+				const long long n1 = std::max<long long> (1, 8 / nchan);
+				r = run_launch (seg_ready / (2 * n1), seg_ready / n1, n1);
+				if (r) return r;
+				r = run_launch (0, seg_ready / wave, wave);
+			} else {
+				r = run_launch (0, seg_ready / wave, wave, true);
+			}
 			if (r) return r;
 			booted = true;
 		}
