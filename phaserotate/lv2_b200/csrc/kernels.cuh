@@ -35,7 +35,12 @@ namespace prk {
 constexpr int kXchFloats = 16 * 32;                                   // Im of lane 31's outputs, per warp
 constexpr int kRedThr    = 24;                                       // slot of the launch's squared filter radius
 constexpr int kRedFloats = 32;                                       // block reductions (filter radius, bootstrap gate)
-constexpr int kSmemBytes = kM * (int)sizeof (float2) + (kXchFloats + 4 + kConvThreads + kRedFloats) * (int)sizeof (float); // + TMEM base address slot + thread ids
+constexpr int kTidOff    = kXchFloats + 4 + kRedFloats;               // lane ids [32] | warp bases [16], see opaque_tid()
+// 133456 bytes: with the 1 KB the system reserves per CTA this stays inside the
+// 132 KB shared-memory carve-out, which leaves 124 KB of L1 to the twiddle
+// tables (measured: every carve-out step up costs 1.5 - 6 % of the kernel)
+constexpr int kSmemBytes = kM * (int)sizeof (float2) + (kTidOff + 48) * (int)sizeof (float);
+static_assert (kSmemBytes + 1024 <= 132 * 1024, "fftconv_kernel must fit the 132 KB carve-out");
 
 enum { EPI_POINTS = 0, EPI_RENDER = 1, EPI_HILBERT = 2 };
 
@@ -96,11 +101,26 @@ struct ConvParams {
 // branch of the epilogue.  `thread (e)` binds the per-thread part of the address
 // once; the returned object is then indexed with compile-time offsets (512 k),
 // which become immediate offsets of the load instructions.
+// The input is streamed: every byte is used once per CTA, so it bypasses L1
+// (no_allocate) and leaves the cache to the twiddle tables, which every segment
+// reads again.
+__device__ __forceinline__ float2 ldg_stream (const float2* p)
+{
+	float2 v;
+	asm volatile ("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+	return v;
+}
+__device__ __forceinline__ float4 ldg_stream (const float4* p)
+{
+	float4 v;
+	asm volatile ("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+	return v;
+}
 struct PlaneLoader { // planar float2 stream
 	const float2* src;
 	struct T {
 		const float2* p;
-		__device__ __forceinline__ float2 operator() (int off) const { return __ldg (p + off); }
+		__device__ __forceinline__ float2 operator() (int off) const { return ldg_stream (p + off); }
 	};
 	__device__ __forceinline__ T thread (int e) const { return T { src + e }; }
 };
@@ -113,7 +133,7 @@ struct Inter2Loader { // stereo: one 16 byte load = frames 2n, 2n+1 of both chan
 		int           chan;
 		__device__ __forceinline__ float2 operator() (int off) const
 		{
-			const float4 v = __ldg (p + off);
+			const float4 v = ldg_stream (p + off);
 			return chan ? make_float2 (v.y, v.w) : make_float2 (v.x, v.z);
 		}
 	};
@@ -300,7 +320,7 @@ __device__ __forceinline__ void epilogue (const float2 (&w)[32], float* xch, uin
 	const int warp  = tid >> 5;
 	const int xbase = warp ? (warp - 1) * 32 : 15 * 32 - 1;
 	if (EPI == EPI_POINTS) {
-		float          thr2   = xch[kXchFloats + 4 + kConvThreads + kRedThr]; // parked in shared memory by the kernel prologue
+		float          thr2   = xch[kXchFloats + 4 + kRedThr]; // parked in shared memory by the kernel prologue
 		float2*        lst    = p.list + (long long)cx.c * p.list_stride;
 		unsigned*      cnt    = p.count + cx.c;
 		const unsigned lt     = lanemask_lt ();
@@ -316,7 +336,7 @@ __device__ __forceinline__ void epilogue (const float2 (&w)[32], float* xch, uin
 				if (in) r2m = fmaxf (r2m, fmaxf (fmaf (p0.x, p0.x, p0.y * p0.y), fmaf (p1.x, p1.x, p1.y * p1.y)));
 			});
 			for (int o = 16; o; o >>= 1) r2m = fmaxf (r2m, __shfl_xor_sync (0xffffffffu, r2m, o));
-			float* red = xch + kXchFloats + 4 + kConvThreads;
+			float* red = xch + kXchFloats + 4;
 			if (lane == 0) red[warp] = r2m;
 			__syncthreads ();
 			if (tid == 0) {
@@ -409,44 +429,44 @@ __device__ __forceinline__ void epilogue (const float2 (&w)[32], float* xch, uin
 	}
 }
 
-// The thread index, re-read from shared memory (volatile) at the start of every
-// pass.  Neither nvcc nor ptxas can see through it, so everything a pass derives
-// from the thread index (addresses, twiddle and filter loads) is recomputed
-// inside the pass instead of being hoisted out of the persistent loop and kept
-// alive - i.e. spilled to local memory - across the other passes, each of which
-// needs the whole register file.
-__device__ __forceinline__ int opaque_tid (const int* tidbuf, int tid)
+// The thread index, re-assembled from two small tables in shared memory
+// (volatile) at the start of every pass.  Neither nvcc nor ptxas can see through
+// it, so everything a pass derives from the thread index (addresses, twiddle
+// and filter loads) is recomputed inside the pass instead of being hoisted out
+// of the persistent loop and kept alive - i.e. spilled to local memory - across
+// the other passes, each of which needs the whole register file.
+__device__ __forceinline__ int opaque_tid (const float* xch, int tid)
 {
-	return *reinterpret_cast<const volatile int*> (tidbuf + tid);
+	const volatile int* tb = reinterpret_cast<const volatile int*> (xch + kTidOff);
+	return tb[tid & 31] + tb[32 + (tid >> 5)];
 }
 
 // One segment: five passes, four shared-memory round trips, epilogue from registers.
 template <int EPI, int NP, class Loader>
 __device__ __forceinline__ void run_segment (float2* sm, float* xch, uint32_t tb, const ConvParams& p, int tid, int lane, EpiCtx& cx, const Loader ld, int reuse_rows = 0)
 {
-	const int* tidbuf = reinterpret_cast<const int*> (xch + kXchFloats + 4);
 	if (EPI != EPI_HILBERT && stash_usable (p.dl)) {
-		p1_forward (sm, p.tw1, opaque_tid (tidbuf, tid), ld, TmemStash { tb }, TmemReuse { tb, reuse_rows, p.V >> 9 });
+		p1_forward (sm, p.tw1, opaque_tid (xch, tid), ld, TmemStash { tb }, TmemReuse { tb, reuse_rows, p.V >> 9 });
 		tmem_wait_st ();
 	} else {
-		p1_forward (sm, p.tw1, opaque_tid (tidbuf, tid), ld);
+		p1_forward (sm, p.tw1, opaque_tid (xch, tid), ld);
 	}
 	__syncthreads ();
 	// the three middle passes of a block pair stay inside one warp (see p2_block())
-	p2_pass<-1> (sm, opaque_tid (tidbuf, tid));
+	p2_pass<-1> (sm, opaque_tid (xch, tid));
 	__syncwarp ();
 	if (NP == 2) {
-		const int t = opaque_tid (tidbuf, tid);
+		const int t = opaque_tid (xch, tid);
 		mid_pass<MID_CONV2> (sm, GTmem { tb }, p.tw2, t, p.scratch + (size_t)blockIdx.x * (kM / 2) + t, reinterpret_cast<const float4*> (p.G),
 		                     reinterpret_cast<const float4*> (p.G1));
 	} else {
-		mid_pass (sm, GTmem { tb }, p.tw2, opaque_tid (tidbuf, tid));
+		mid_pass (sm, GTmem { tb }, p.tw2, opaque_tid (xch, tid));
 	}
 	__syncwarp ();
-	p2_pass<+1> (sm, opaque_tid (tidbuf, tid));
+	p2_pass<+1> (sm, opaque_tid (xch, tid));
 	__syncthreads ();
 	float2 w[32];
-	p1_inverse (sm, p.tw1, opaque_tid (tidbuf, tid), w);
+	p1_inverse (sm, p.tw1, opaque_tid (xch, tid), w);
 	if (lane == 31) {
 		float* x = xch + (tid >> 5) * 32;
 #pragma unroll
@@ -461,12 +481,11 @@ __device__ __forceinline__ void run_segment (float2* sm, float* xch, uint32_t tb
 template <class Loader>
 __device__ __noinline__ void spectrum_only (float2* sm, const float* xch, const float2* tw1, const float2* tw2, float4* scr, int tid, const Loader ld)
 {
-	const int* tidbuf = reinterpret_cast<const int*> (xch + kXchFloats + 4);
-	p1_forward (sm, tw1, opaque_tid (tidbuf, tid), ld);
+	p1_forward (sm, tw1, opaque_tid (xch, tid), ld);
 	__syncthreads ();
-	p2_pass<-1> (sm, opaque_tid (tidbuf, tid));
+	p2_pass<-1> (sm, opaque_tid (xch, tid));
 	__syncwarp ();
-	const int t = opaque_tid (tidbuf, tid);
+	const int t = opaque_tid (xch, tid);
 	mid_pass<MID_SPECTRUM> (sm, GTable { nullptr, 0, 0 }, tw2, t, scr + t);
 	__syncthreads (); // every warp is done reading sm
 }
@@ -483,7 +502,8 @@ __global__ void __launch_bounds__ (kConvThreads, 1) fftconv_kernel (const ConvPa
 	extern __shared__ __align__ (16) float2 sm[];
 	float*    xch  = reinterpret_cast<float*> (sm + kM);
 	const int tid  = threadIdx.x;
-	reinterpret_cast<int*> (xch + kXchFloats + 4)[tid] = tid; // see opaque_tid(); made visible by the barrier in tmem_alloc_all()
+	if (tid < 32) reinterpret_cast<int*> (xch + kTidOff)[tid] = tid;                  // see opaque_tid(); made visible by the
+	else if (tid < 48) reinterpret_cast<int*> (xch + kTidOff)[tid] = 32 * (tid - 32); // barrier in tmem_alloc_all()
 	const uint32_t tmem = tmem_alloc_all (reinterpret_cast<uint32_t*> (xch + kXchFloats), tid);
 	const uint32_t tb   = tmem_thread_base (tmem, tid);
 	const int lane = tid & 31;
@@ -493,7 +513,7 @@ __global__ void __launch_bounds__ (kConvThreads, 1) fftconv_kernel (const ConvPa
 		// filter radius of this launch: thr2 = (min_a peaks[c][a])^2 (1 - 1e-5), see
 		// threshold_kernel; parked in shared memory for the epilogues
 		const int cc  = p.chan0 + (int)blockIdx.x % p.nchan;
-		float*    red = xch + kXchFloats + 4 + kConvThreads;
+		float*    red = xch + kXchFloats + 4;
 		float     t2  = 0.f;
 		if (p.thr_mode < 0) {
 			t2 = p.thr2[cc];

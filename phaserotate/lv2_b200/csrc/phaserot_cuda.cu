@@ -372,6 +372,9 @@ launch_conv_np (phaserot* h, const ConvParams& p)
 	static bool attr_done = false; // one flag per template instantiation
 	if (!attr_done) {
 		CK (cudaFuncSetAttribute (fftconv_kernel<EPI, SRC, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+		if (getenv ("PHASEROT_CARVEOUT")) {
+			CK (cudaFuncSetAttribute (fftconv_kernel<EPI, SRC, NP>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi (getenv ("PHASEROT_CARVEOUT"))));
+		}
 		attr_done = true;
 	}
 	const long long total = p.nseg * p.nchan;
