@@ -94,6 +94,8 @@ struct ConvParams {
 	const float2* ramp;         // [n_chan][ramp_stride] per-sample (ca, sa) for t < ramp_len[c]
 	long long     ramp_stride;
 	const int*    ramp_len;     // [n_chan] (in samples, even) or nullptr
+	float*        out_inter;    // EPI_RENDER: interleaved destination [out_frames][C] instead of `out` (fused CLI render)
+	long long     out_frames;
 	int           out_compact;  // EPI_HILBERT: segment j of the launch writes its V outputs at out[8 + j V ..) (true-peak staging)
 };
 
@@ -409,10 +411,10 @@ __device__ __forceinline__ void epilogue (const float2 (&w)[32], float* xch, uin
 				float     pv = __shfl_up_sync (0xffffffffu, w[k].y, 1);
 				if (lane == 0) pv = xch[xbase + k];
 				if (ok[kk]) {
-					float2 y = make_float2 (pv, w[k].x);
+					float2          y  = make_float2 (pv, w[k].x);
+					const long long t0 = 2 * (cx.mbase + i);
 					if (EPI == EPI_RENDER) {
-						float2          cs0 = cs, cs1 = cs;
-						const long long t0  = 2 * (cx.mbase + i);
+						float2 cs0 = cs, cs1 = cs;
 						if (t0 < rlen) {
 							const float2* r = p.ramp + (long long)cx.c * p.ramp_stride + t0;
 							cs0             = r[0];
@@ -422,7 +424,15 @@ __device__ __forceinline__ void epilogue (const float2 (&w)[32], float* xch, uin
 						y.x = __fadd_rn (__fmul_rn (cs0.x, zd[kk].x), __fmul_rn (cs0.y, pv));
 						y.y = __fadd_rn (__fmul_rn (cs1.x, zd[kk].y), __fmul_rn (cs1.y, w[k].x));
 					}
-					__stcs (outc + i, y);
+					if (EPI == EPI_RENDER && p.out_inter) {
+						// straight into the interleaved frames (plain stores: the CTAs of the
+						// other channels fill the rest of each sector side by side, L2 merges them)
+						float* o = p.out_inter + t0 * p.C + cx.c;
+						if (t0 < p.out_frames) o[0] = y.x;
+						if (t0 + 1 < p.out_frames) o[p.C] = y.y;
+					} else {
+						__stcs (outc + i, y);
+					}
 				}
 			}
 		}

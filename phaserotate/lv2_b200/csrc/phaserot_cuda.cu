@@ -885,23 +885,35 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 }
 
 /*
- * Render stream: y[t] = ca x[t - L/2] + sa H[t] for t in [0, t_end), planar
- * result left in d_out (float2 per two samples).
+ * Render stream: y[t] = ca x[t - L/2] + sa H[t] for t in [0, t_end).
+ *   d_dst_inter == nullptr   planar result left in d_out (float2 per two samples; plugin bulk path)
+ *   d_dst_inter != nullptr   fused CLI render: the FFT kernel reads the interleaved frames in place
+ *                            and writes interleaved frames [0, t_end) to d_dst_inter (device) - one
+ *                            pass over the audio, 8 bytes per sample
  */
 int
 render_core (phaserot* h, const float* src, bool src_is_device, long long n_frames, long long t_end, const float* hist,
              const float2* chan_cs /*host [C]*/, const float2* ramp /*host [C][ramp_stride] or null*/, long long ramp_stride,
-             const int* ramp_len /*host [C] or null*/, long long* m_end_out)
+             const int* ramp_len /*host [C] or null*/, long long* m_end_out, float* d_dst_inter = nullptr)
 {
 	const long long m_end = (t_end + 1) / 2;
-	long long       nseg  = 0;
-	int             rc    = ensure_planes (h, m_end, &nseg);
-	if (rc) return rc;
-	rc = init_front_pad (h, hist);
-	if (rc) return rc;
-	h->out_stride = (m_end + 3) & ~3LL;
-	rc            = h->d_out.ensure (sizeof (float2) * (size_t)h->out_stride * h->C);
-	if (rc) return rc;
+	long long       nseg  = (m_end + h->V - 1) / h->V;
+	int             rc    = PHASEROT_OK;
+	const float*    d_hist = nullptr;
+	if (!d_dst_inter) {
+		rc = ensure_planes (h, m_end, &nseg);
+		if (rc) return rc;
+		rc = init_front_pad (h, hist);
+		if (rc) return rc;
+		h->out_stride = (m_end + 3) & ~3LL;
+		rc            = h->d_out.ensure (sizeof (float2) * (size_t)h->out_stride * h->C);
+		if (rc) return rc;
+	} else if (hist) {
+		rc = h->d_hist.ensure (sizeof (float) * (size_t)h->L * h->C);
+		if (rc) return rc;
+		CK (cudaMemcpyAsync (h->d_hist.p, hist, sizeof (float) * (size_t)h->L * h->C, cudaMemcpyHostToDevice, h->stream));
+		d_hist = (const float*)h->d_hist.p;
+	}
 	rc = h->d_chancs.ensure (sizeof (float2) * (size_t)h->C);
 	if (rc) return rc;
 	CK (cudaMemcpyAsync (h->d_chancs.p, chan_cs, sizeof (float2) * (size_t)h->C, cudaMemcpyHostToDevice, h->stream));
@@ -913,11 +925,8 @@ render_core (phaserot* h, const float* src, bool src_is_device, long long n_fram
 	}
 	CK (cudaStreamSynchronize (h->stream)); // small host arrays above may be stack buffers
 
-	const long long n_fill = nseg * h->V;
-	if (src_is_device) {
-		rc = launch_deinterleave (h, src, 0, n_frames, 0, n_fill);
-		if (rc) return rc;
-	} else {
+	const float* d_src = src;
+	if (!src_is_device) {
 		const size_t bytes = sizeof (float) * (size_t)n_frames * h->C;
 		rc                 = h->d_io.ensure (std::max<size_t> (bytes, 16));
 		if (rc) return rc;
@@ -925,7 +934,10 @@ render_core (phaserot* h, const float* src, bool src_is_device, long long n_fram
 			CK (cudaMemcpyAsync (h->d_io.p, src, bytes, cudaMemcpyHostToDevice, h->stream));
 			h->stats.h2d_bytes += bytes;
 		}
-		rc = launch_deinterleave (h, (const float*)h->d_io.p, 0, n_frames, 0, n_fill);
+		d_src = (const float*)h->d_io.p;
+	}
+	if (!d_dst_inter) {
+		rc = launch_deinterleave (h, d_src, 0, n_frames, 0, nseg * h->V);
 		if (rc) return rc;
 	}
 	ConvParams p;
@@ -941,7 +953,17 @@ render_core (phaserot* h, const float* src, bool src_is_device, long long n_fram
 	p.ramp        = (ramp && ramp_len) ? (const float2*)h->d_ramp.p : nullptr;
 	p.ramp_stride = ramp_stride;
 	p.ramp_len    = (ramp && ramp_len) ? d_ramplen (h) : nullptr;
-	rc            = launch_conv<EPI_RENDER> (h, p);
+	if (d_dst_inter) {
+		p.inter      = d_src;
+		p.hist       = d_hist;
+		p.n_frames   = n_frames;
+		p.C          = h->C;
+		p.out_inter  = d_dst_inter;
+		p.out_frames = t_end;
+		rc           = launch_conv<EPI_RENDER, SRC_INTER> (h, p);
+	} else {
+		rc = launch_conv<EPI_RENDER> (h, p);
+	}
 	if (rc) return rc;
 	*m_end_out = m_end;
 	return PHASEROT_OK;
@@ -1492,15 +1514,13 @@ phaserot_apply (phaserot_t* h, float* buf, const int* angles)
 	std::vector<float2> cs;
 	angles_to_cs (h, angles, cs);
 	long long m_end = 0;
-	int       rc    = render_core (h, buf, false, h->L, h->L, h->ap_hist.data (), cs.data (), nullptr, 0, nullptr, &m_end);
+	int       rc    = h->d_stage[0].ensure (sizeof (float) * (size_t)h->L * h->C);
+	if (rc) return rc;
+	rc = render_core (h, buf, false, h->L, h->L, h->ap_hist.data (), cs.data (), nullptr, 0, nullptr, &m_end, (float*)h->d_stage[0].p);
 	if (rc) return rc;
 	// remember the input block as history (cli:461) before it is overwritten
 	memcpy (h->ap_hist.data (), buf, sizeof (float) * (size_t)h->L * h->C);
-	rc = h->d_io.ensure (sizeof (float) * (size_t)h->L * h->C);
-	if (rc) return rc;
-	rc = launch_interleave (h, m_end, 0, (float*)h->d_io.p, h->L);
-	if (rc) return rc;
-	CK (cudaMemcpyAsync (buf, h->d_io.p, sizeof (float) * (size_t)h->L * h->C, cudaMemcpyDeviceToHost, h->stream));
+	CK (cudaMemcpyAsync (buf, h->d_stage[0].p, sizeof (float) * (size_t)h->L * h->C, cudaMemcpyDeviceToHost, h->stream));
 	CK (cudaStreamSynchronize (h->stream));
 	h->stats.d2h_bytes += sizeof (float) * (size_t)h->L * h->C;
 	return PHASEROT_OK;
@@ -1524,8 +1544,15 @@ render_bulk (phaserot* h, const float* src, bool dev_in, uint64_t n_frames, cons
 	if (t_end == 0) {
 		return PHASEROT_OK;
 	}
-	long long m_end = 0;
-	int       rc    = render_core (h, src, dev_in, F, t_end, nullptr, cs.data (), nullptr, 0, nullptr, &m_end);
+	long long    m_end = 0;
+	const size_t bytes = sizeof (float) * (size_t)t_end * h->C;
+	int          rc    = PHASEROT_OK;
+	if (!dev_out) {
+		// d_io holds the uploaded input; the staging buffer takes the output
+		rc = h->d_stage[0].ensure (bytes);
+		if (rc) return rc;
+	}
+	rc = render_core (h, src, dev_in, F, t_end, nullptr, cs.data (), nullptr, 0, nullptr, &m_end, dev_out ? dst : (float*)h->d_stage[0].p);
 	if (rc) return rc;
 	// stream state for a following apply(): the last block that went in
 	std::fill (h->ap_hist.begin (), h->ap_hist.end (), 0.f);
@@ -1538,14 +1565,8 @@ render_bulk (phaserot* h, const float* src, bool dev_in, uint64_t n_frames, cons
 		CK (cudaStreamSynchronize (h->stream));
 	}
 	if (dev_out) {
-		return launch_interleave (h, m_end, 0, dst, t_end);
+		return PHASEROT_OK;
 	}
-	const size_t bytes = sizeof (float) * (size_t)t_end * h->C;
-	// d_io may hold the uploaded input; use the staging buffer for the output
-	rc = h->d_stage[0].ensure (bytes);
-	if (rc) return rc;
-	rc = launch_interleave (h, m_end, 0, (float*)h->d_stage[0].p, t_end);
-	if (rc) return rc;
 	CK (cudaMemcpyAsync (dst, h->d_stage[0].p, bytes, cudaMemcpyDeviceToHost, h->stream));
 	CK (cudaStreamSynchronize (h->stream));
 	h->stats.d2h_bytes += bytes;
