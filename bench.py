@@ -363,24 +363,34 @@ def gpu_main(args):
         prev = gen_chunk_torch(torch, chunk0 - 1, dev)
         # the previous rank's shard ends at frame `frames` of its own chunk range
         prev_tail_end = frames - (n_chunks - 1) * GEN_CHUNK
-        hist = prev[prev_tail_end - BLKSIZ:prev_tail_end].contiguous().cpu().numpy()
+        hist = prev[prev_tail_end - BLKSIZ:prev_tail_end].contiguous()  # stays on the device, read in place
+    hist_ptr = hist.data_ptr() if hist is not None else None
     torch.cuda.synchronize()
 
     h = capi.Phaserot(mode=capi.MODE_CLI, n_channels=CHANNELS, blksiz=BLKSIZ, subsample=args.subsample, device=local,
                       flags=capi.FLAG_NO_PRUNE if args.no_prune else 0)
     stream = torch.cuda.current_stream()
     h.set_stream(stream.cuda_stream)
-    peaks_dev = torch.zeros((CHANNELS, A), device=dev, dtype=torch.float32)
+    tables = {}
+
+    def combine_shards(handle):
+        """NCCL max all-reduce, in place, on the handle's device-resident table of the pending
+        sweep (per-angle maxima + raw peaks; phaserot_pending_table): no host round trip."""
+        ptr, nc, na = handle.pending_table()
+        n = nc * na + nc
+        t = tables.get((ptr, n))
+        if t is None:
+            class _Dev:
+                __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+            t = tables[(ptr, n)] = torch.as_tensor(_Dev(), device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
 
     def step_device():
         h.reset()
-        h.sweep_shard_device(x.data_ptr(), frames, hist, rank == 0, rank == world - 1)
-        pk = h.peaks()  # sync + D2H of the table
+        h.sweep_shard_device(x.data_ptr(), frames, hist_ptr, rank == 0, rank == world - 1)
         if world > 1:
-            peaks_dev.copy_(torch.from_numpy(pk), non_blocking=False)
-            dist.all_reduce(peaks_dev, op=dist.ReduceOp.MAX)
-            return peaks_dev
-        return pk
+            combine_shards(h)
+        return h.peaks()  # sync + D2H of the (combined) table
 
     def barrier():
         if world > 1:
@@ -426,6 +436,8 @@ def gpu_main(args):
     torch.cuda.synchronize()
     he = capi.Phaserot(mode=capi.MODE_CLI, n_channels=CHANNELS, blksiz=BLKSIZ, subsample=args.subsample, device=local,
                        flags=capi.FLAG_NO_PRUNE if args.no_prune else 0)
+    if world > 1:
+        he.set_stream(stream.cuda_stream)  # the upload, the sweep and the all-reduce are ordered on one stream
 
     def step_e2e():
         he.reset()
@@ -434,11 +446,9 @@ def gpu_main(args):
         else:
             # shard semantics need history: upload then shard call (H2D still inside the step)
             x.copy_(xh, non_blocking=True)
-            he.sweep_shard_device(x.data_ptr(), frames, hist, rank == 0, rank == world - 1)
-        pk = he.peaks()
-        if world > 1:
-            peaks_dev.copy_(torch.from_numpy(pk))
-            dist.all_reduce(peaks_dev, op=dist.ReduceOp.MAX)
+            he.sweep_shard_device(x.data_ptr(), frames, hist_ptr, rank == 0, rank == world - 1)
+            combine_shards(he)
+        he.peaks()
 
     for _ in range(2):
         step_e2e()

@@ -32,7 +32,7 @@ extern "C" {
 #define PHASEROT_API __attribute__ ((visibility ("default")))
 #endif
 
-#define PHASEROT_ABI_VERSION 2
+#define PHASEROT_ABI_VERSION 3
 
 typedef struct phaserot phaserot_t;
 
@@ -140,7 +140,8 @@ PHASEROT_API int phaserot_sweep_device (phaserot_t* h, const float* d_interleave
 /* One shard of a longer stream, for sample-range sharding across GPUs: this
  * handle examines output samples of frames [0, n_frames) of the shard, where
  * the shard is preceded in the full stream by `hist` (blksiz frames,
- * interleaved, HOST memory; NULL = silence / start of stream).
+ * interleaved, host or device memory; NULL = silence / start of stream; a
+ * device pointer is read in place and must stay valid until the table is read).
  *   first != 0 : the shard starts the stream (first-block rule applies)
  *   last  != 0 : the shard ends it (short block zero padded + zero flush block)
  * Non-last shards must be a multiple of blksiz long.  Because a per-angle peak
@@ -154,6 +155,19 @@ PHASEROT_API int phaserot_sweep_shard_device (phaserot_t* h, const float* d_inte
                                               int ang_start, int ang_end, int ang_stride, int chn);
 
 PHASEROT_API uint32_t phaserot_shard_align (const phaserot_t* h);
+
+/* Device-resident result of the sweep that is still pending (enqueued, not read
+ * back yet), for combining shards without a host round trip: *d_table points at
+ * n_channels * n_angles + n_channels floats owned by the handle - the running
+ * per-angle maxima [channel][angle slot] followed by the raw input peak of every
+ * channel (the value of grid index 0, cli:413-414).  All values are >= 0, so an
+ * element-wise max over the shards' buffers (NCCL all-reduce, ncclMax, in place,
+ * enqueued after the sweep on the handle's stream) is the result of the whole
+ * stream; the next phaserot_peak()/phaserot_peaks()/phaserot_sync() then reads
+ * the combined table back on every rank.  Replaces the merge of the per-thread
+ * `_peak` rows in PhaseRotate::analyze (cli:431-444) across devices.
+ * PHASEROT_E_STATE when no sweep is pending. */
+PHASEROT_API int phaserot_pending_table (phaserot_t* h, float** d_table, int* n_channels, int* n_angles);
 
 /* Block-streaming drop-in for PhaseRotate::analyze (cli:431-444): feed one
  * block of blksiz frames at a time (`start` != 0 for the first block of a

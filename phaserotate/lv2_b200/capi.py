@@ -16,14 +16,14 @@ E_INVAL, E_NO_DEVICE, E_CUDA, E_NOMEM, E_UNSUPPORTED, E_STATE = -1, -2, -3, -4, 
 MODE_CLI, MODE_PLUGIN = 0, 1
 FLAG_NO_FIRST_BLOCK_QUIRK = 1
 FLAG_NO_PRUNE = 2
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 SYMBOLS = [
     "phaserot_create", "phaserot_destroy", "phaserot_reset", "phaserot_set_stream",
     "phaserot_sweep", "phaserot_sweep_device", "phaserot_analyze", "phaserot_peak", "phaserot_peaks", "phaserot_lut",
     "phaserot_apply", "phaserot_render", "phaserot_render_device",
     "phaserot_process", "phaserot_latency",
-    "phaserot_sweep_shard_device", "phaserot_shard_align", "phaserot_set_profiling", "phaserot_get_kernel_times",
+    "phaserot_sweep_shard_device", "phaserot_shard_align", "phaserot_pending_table", "phaserot_set_profiling", "phaserot_get_kernel_times",
     "phaserot_sync", "phaserot_get_stats", "phaserot_reset_stats",
     "phaserot_alloc_host", "phaserot_free_host",
     "phaserot_strerror", "phaserot_last_error", "phaserot_abi_version",
@@ -94,6 +94,7 @@ def load():
     lib.phaserot_latency.restype = C.c_uint32
     lib.phaserot_sweep_shard_device.argtypes = [vp, vp, C.c_uint64, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.phaserot_shard_align.argtypes = [vp]
+    lib.phaserot_pending_table.argtypes = [vp, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.phaserot_shard_align.restype = C.c_uint32
     lib.phaserot_set_profiling.argtypes = [vp, C.c_int]
     lib.phaserot_get_kernel_times.argtypes = [vp, C.POINTER(KTimes)]
@@ -178,16 +179,24 @@ class Phaserot:
         self._ck(self._lib.phaserot_sweep_device(self._h, C.c_void_p(dev_ptr), n_frames, ang_start, ang_end, stride, chn), "phaserot_sweep_device")
 
     def sweep_shard_device(self, dev_ptr, n_frames, hist, first, last, ang_start=0, ang_end=None, stride=1, chn=-1):
-        """hist: host array [blksiz, channels] float32 or None."""
+        """hist: host array [blksiz, channels] float32, an int (device pointer to the same) or None."""
         if ang_end is None:
             ang_end = self.maxsample
         hp = None
-        if hist is not None:
+        if isinstance(hist, int):
+            hp = C.c_void_p(hist)
+        elif hist is not None:
             hist = np.ascontiguousarray(hist, np.float32)
             assert hist.size == self.blksiz * self.n_channels
             hp = _ptr(hist)
         self._ck(self._lib.phaserot_sweep_shard_device(self._h, C.c_void_p(dev_ptr), n_frames, hp, int(first), int(last),
                                                        ang_start, ang_end, stride, chn), "phaserot_sweep_shard_device")
+
+    def pending_table(self):
+        """(device pointer, n_channels, n_angles) of the pending sweep's table: n_channels * n_angles + n_channels floats."""
+        p, nc, na = C.POINTER(C.c_float)(), C.c_int(), C.c_int()
+        self._ck(self._lib.phaserot_pending_table(self._h, C.byref(p), C.byref(nc), C.byref(na)), "phaserot_pending_table")
+        return C.cast(p, C.c_void_p).value, nc.value, na.value
 
     def shard_align(self):
         return int(self._lib.phaserot_shard_align(self._h))

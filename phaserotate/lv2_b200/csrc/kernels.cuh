@@ -66,6 +66,8 @@ struct ConvParams {
 	int           chan0;        // first channel of this launch
 	long long     seg0;         // first segment
 	long long     seg_stride;   // segment index step (1 = contiguous; > 1 = sparse bootstrap sample)
+	int           seg_jitter;   // sparse sample: pseudo-random offset in [0, seg_stride) per segment, so that the
+	                            // sample cannot lock onto a periodic envelope of the programme
 	long long     nseg;         // segments per channel in this launch
 	int           nchan;
 	long long     m_end;        // outputs exist for complex index m < m_end
@@ -573,7 +575,7 @@ __global__ void __launch_bounds__ (kConvThreads, 1) fftconv_kernel (const ConvPa
 	const int c = p.chan0 + ci;
 	bool prev_inside = false;
 	for (int si = s_begin; si < s_end; ++si) {
-		const long long seg = p.seg0 + si * p.seg_stride;
+		const long long seg = p.seg0 + si * p.seg_stride + (p.seg_jitter ? (long long)(((unsigned)si * 2654435761u >> 8) % (unsigned)p.seg_stride) : 0);
 		const long long n0  = seg * p.V - p.Lh; // complex stream index of local index 0
 		if (NP == 2 && (si == s_begin || p.seg_stride != 1)) {
 			// the scratch does not hold the spectrum of segment seg - 1 yet
@@ -705,6 +707,7 @@ __global__ void __launch_bounds__ (256) sweep_kernel (const float2* __restrict__
 	__shared__ __align__ (16) float2 tile[kSweepTile];
 	const int       c    = chan0 + blockIdx.z;
 	const unsigned  n    = count[c];
+	if (blockIdx.x * kSweepTile >= n) return; // most launches see a few dozen survivors: nothing for this CTA
 	const float2*   pts  = list + (long long)c * list_stride;
 	const int       a0   = blockIdx.y * (blockDim.x * R) + threadIdx.x;
 

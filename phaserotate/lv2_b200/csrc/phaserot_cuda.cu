@@ -203,7 +203,7 @@ struct phaserot {
 	DevBuf d_tpH; // true-peak staging of the Hilbert branch: [C][tp_stride] floats
 	long long tp_stride = 0;
 	int       OS        = 1; // 1 = digital peak, 2 / 4 = oversampled true-peak
-	PinBuf h_stage[2], h_res, h_io;
+	PinBuf h_stage[2], h_res, h_io, h_cs;
 	long long plane_stride = 0, out_stride = 0, list_stride = 0;
 
 	// pending (asynchronous) sweep result
@@ -305,7 +305,9 @@ prof_resolve (phaserot* h)
 
 unsigned*           d_count (phaserot* h) { return (unsigned*)h->d_small.p; }
 float*              d_thr2 (phaserot* h) { return (float*)h->d_small.p + 64; }
-unsigned*           d_raw (phaserot* h) { return (unsigned*)h->d_small.p + 128; }
+// raw input peaks [C]: directly behind the [C][A] table of the pending sweep, so that table and
+// raw peaks are one contiguous buffer (one D2H copy, one all-reduce when shards are combined)
+unsigned*           d_raw (phaserot* h) { return (unsigned*)h->d_peaks.p + (size_t)std::max (h->pend_A, 1) * h->C; }
 int*                d_ramplen (phaserot* h) { return (int*)h->d_small.p + 192; }
 unsigned long long* d_stats (phaserot* h) { return (unsigned long long*)((char*)h->d_small.p + 4 * 64 * sizeof (int)); }
 unsigned*           d_count_odd (phaserot* h) { return (unsigned*)((char*)h->d_small.p + 4 * 64 * sizeof (int) + 2 * sizeof (unsigned long long)); }
@@ -514,9 +516,10 @@ finish_pending (phaserot* h)
 	if (rc) return rc;
 	unsigned* res = (unsigned*)h->h_res.p;
 	if (A > 0) {
-		CK (cudaMemcpyAsync (res, h->d_peaks.p, sizeof (unsigned) * (size_t)A * h->C, cudaMemcpyDeviceToHost, h->stream));
+		CK (cudaMemcpyAsync (res, h->d_peaks.p, sizeof (unsigned) * ((size_t)A * h->C + (size_t)h->C), cudaMemcpyDeviceToHost, h->stream));
+	} else {
+		CK (cudaMemcpyAsync (res, d_raw (h), sizeof (unsigned) * (size_t)h->C, cudaMemcpyDeviceToHost, h->stream));
 	}
-	CK (cudaMemcpyAsync (res + (size_t)A * h->C, d_raw (h), sizeof (unsigned) * (size_t)h->C, cudaMemcpyDeviceToHost, h->stream));
 	unsigned long long* st = (unsigned long long*)(res + (size_t)A * h->C + (size_t)h->C + (((size_t)A * h->C + h->C) & 1));
 	CK (cudaMemcpyAsync (st, d_stats (h), 2 * sizeof (unsigned long long), cudaMemcpyDeviceToHost, h->stream));
 	CK (cudaStreamSynchronize (h->stream));
@@ -603,11 +606,16 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 	}
 	rc = h->d_cs.ensure (sizeof (float2) * cs.size ());
 	if (rc) return rc;
-	rc = h->d_peaks.ensure (sizeof (unsigned) * (size_t)std::max (A, 1) * h->C);
+	rc = h->d_peaks.ensure (sizeof (unsigned) * ((size_t)std::max (A, 1) * h->C + (size_t)h->C));
 	if (rc) return rc;
-	CK (cudaMemcpyAsync (h->d_cs.p, cs.data (), sizeof (float2) * cs.size (), cudaMemcpyHostToDevice, h->stream));
-	CK (cudaStreamSynchronize (h->stream)); // cs is a stack-lifetime buffer
-	CK (cudaMemsetAsync (h->d_peaks.p, 0, sizeof (unsigned) * (size_t)std::max (A, 1) * h->C, h->stream));
+	// staged through a pinned buffer of the handle: no synchronisation (the stream is
+	// idle with respect to the previous pass: finish_pending() above waited for it)
+	rc = h->h_cs.ensure (sizeof (float2) * cs.size ());
+	if (rc) return rc;
+	memcpy (h->h_cs.p, cs.data (), sizeof (float2) * cs.size ());
+	CK (cudaMemcpyAsync (h->d_cs.p, h->h_cs.p, sizeof (float2) * cs.size (), cudaMemcpyHostToDevice, h->stream));
+	h->pend_A = A; // d_raw() depends on it
+	CK (cudaMemsetAsync (h->d_peaks.p, 0, sizeof (unsigned) * ((size_t)std::max (A, 1) * h->C + (size_t)h->C), h->stream));
 	CK (cudaMemsetAsync (h->d_small.p, 0, kSmallBytes, h->stream));
 
 	const long long m_end = (t_end + 1) / 2;
@@ -615,11 +623,18 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 	const float*    d_hist = nullptr;
 	if (hist) {
 		// frames [-L, 0) of the stream, read by the segments that reach before its start
-		rc = h->d_hist.ensure (sizeof (float) * (size_t)h->L * h->C);
-		if (rc) return rc;
-		CK (cudaMemcpyAsync (h->d_hist.p, hist, sizeof (float) * (size_t)h->L * h->C, cudaMemcpyHostToDevice, h->stream));
-		CK (cudaStreamSynchronize (h->stream));
-		d_hist = (const float*)h->d_hist.p;
+		cudaPointerAttributes at;
+		const bool on_device = cudaPointerGetAttributes (&at, hist) == cudaSuccess && at.type == cudaMemoryTypeDevice;
+		cudaGetLastError ();
+		if (on_device) {
+			d_hist = hist; // read in place (the caller keeps it alive until the table is read back)
+		} else {
+			rc = h->d_hist.ensure (sizeof (float) * (size_t)h->L * h->C);
+			if (rc) return rc;
+			CK (cudaMemcpyAsync (h->d_hist.p, hist, sizeof (float) * (size_t)h->L * h->C, cudaMemcpyHostToDevice, h->stream));
+			CK (cudaStreamSynchronize (h->stream));
+			d_hist = (const float*)h->d_hist.p;
+		}
 	}
 
 	// survivor list: one launch covers at most `segs_max` segments per channel
@@ -746,6 +761,7 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 			p.count       = parity ? d_count_odd (h) : d_count (h);
 			p.count_reset = parity ? d_count (h) : d_count_odd (h);
 			p.boot_beta   = boot ? kBootBeta : 0.f;
+			p.seg_jitter  = boot && stride > 1;
 			r = launch_conv<EPI_POINTS, SRC_INTER> (h, p);
 			if (r) return r;
 			if (A > 0) {
@@ -788,7 +804,9 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 		const long long seg_ready = final ? nseg : std::min (nseg, frames_ready / (2 * (long long)h->V));
 		if (!booted && seg_ready >= 2 * wave) {
 			// Bootstrap the filter radius from a sparse sample of the segments
-			// available so far.  Digital peak: one wave spread over the range, of
+			// available so far.  Digital peak: one wave spread over the range (with a
+			// pseudo-random offset per segment: a regular grid once locked onto the
+			// slow envelope of the programme and saw only its quiet phase), of
 			// which only the strongest points (squared radius within kBootBeta of the
 			// largest one the launch has seen) are swept - a few hundred well-spread
 			// strong points already put every angle's running peak close to its
@@ -1447,6 +1465,21 @@ phaserot_sweep_shard_device (phaserot_t* h, const float* d_interleaved, uint64_t
 	const long long B     = (F + h->L - 1) / h->L;
 	const long long t_end = last ? (B + 1) * h->L : F;
 	return sweep_core (h, d_interleaved, true, F, t_end, first != 0 && B > 0, hist, ang_start, ang_end, ang_stride, chn);
+}
+
+int
+phaserot_pending_table (phaserot_t* h, float** d_table, int* n_channels, int* n_angles)
+{
+	if (!h || !d_table || !n_channels || !n_angles) {
+		return PHASEROT_E_INVAL;
+	}
+	if (!h->pending) {
+		return PHASEROT_E_STATE;
+	}
+	*d_table    = (float*)h->d_peaks.p;
+	*n_channels = h->C;
+	*n_angles   = std::max (h->pend_A, 1);
+	return PHASEROT_OK;
 }
 
 float

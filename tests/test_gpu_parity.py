@@ -214,6 +214,54 @@ def test_full_size_pruned_equals_brute_force_and_shards_combine():
         assert rel(np.maximum(a, h.peaks()), brute) <= 2e-6
 
 
+def test_pending_table_on_device_and_device_history():
+    """phaserot_pending_table: the device-resident table (per-angle maxima, then raw peaks) is what
+    phaserot_peaks reads back; combining two shards by an element-wise max written INTO the second
+    handle's device table (what the NCCL max all-reduce does in place) yields the whole-stream table.
+    The shard history may be a device pointer."""
+    import torch
+    import bench
+    x, frames = _device_programme(120.0)
+    with capi.Phaserot(n_channels=2, blksiz=bench.BLKSIZ, subsample=10) as h:
+        with pytest.raises(capi.PhaserotError):
+            h.pending_table()              # nothing pending
+        h.sweep_device(x.data_ptr(), frames)
+        ptr, nc, na = h.pending_table()
+        assert (nc, na) == (2, h.maxsample - 1)
+
+        class _Dev:
+            __cuda_array_interface__ = {"shape": (nc * na + nc,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+        t = torch.as_tensor(_Dev(), device=x.device)
+        torch.cuda.synchronize()
+        snap = t.clone().cpu().numpy()
+        whole = h.peaks()
+        assert np.array_equal(snap[:nc * na].reshape(nc, na), whole[:, 1:])
+        assert np.array_equal(snap[nc * na:], whole[:, 0])
+        al = h.shard_align()
+        half = (frames // 2) - ((frames // 2) % al)
+        h.reset()
+        h.sweep_shard_device(x.data_ptr(), half, None, True, False)
+        ptr_a, _, _ = h.pending_table()
+
+        class _DevA:
+            __cuda_array_interface__ = {"shape": (nc * na + nc,), "typestr": "<f4", "data": (ptr_a, False), "version": 2}
+        torch.cuda.synchronize()
+        first = torch.as_tensor(_DevA(), device=x.device).clone()
+        h.peaks()
+        h.reset()
+        hist = x[half - bench.BLKSIZ:half].contiguous()
+        h.sweep_shard_device(x[half:].data_ptr(), frames - half, hist.data_ptr(), False, True)   # device history
+        ptr_b, _, _ = h.pending_table()
+
+        class _DevB:
+            __cuda_array_interface__ = {"shape": (nc * na + nc,), "typestr": "<f4", "data": (ptr_b, False), "version": 2}
+        torch.cuda.synchronize()
+        tb = torch.as_tensor(_DevB(), device=x.device)
+        tb.copy_(torch.maximum(tb, first))     # in-place combine on the device
+        torch.cuda.synchronize()
+        assert np.array_equal(h.peaks(), whole)
+
+
 def test_blksiz_32768_pruned_equals_brute_force_and_shards_combine():
     """FIR length 32768 (two tap partitions): 2 min stereo at 0.1 deg, same properties as above."""
     L = 32768
