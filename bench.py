@@ -301,6 +301,26 @@ def secondary_legs(torch, capi, dev, local, x, frames, hbm_peak):
         dt = time.perf_counter() - t0
         out["plugin_bulk"] = {"value": nb / dt / 1e6, "unit": "rotated Msamples/s", "ms_per_call": 1e3 * dt,
                               "workload": "LV2 run(): mono 48 kHz, one 600 s call, pageable host buffers in and out"}
+    # -- end to end from a 16-bit PCM file image: the headline workload quantised to int16 in
+    #    pinned host memory, through phaserot_sweep_pcm (H2D of 2 bytes per sample + widening on the device)
+    q = torch.empty((frames, CHANNELS), dtype=torch.int16, pin_memory=True)
+    q.copy_((x * 32768.0).round().clamp_(-32768, 32767).to(torch.int16))
+    torch.cuda.synchronize()
+    with capi.Phaserot(mode=capi.MODE_CLI, n_channels=CHANNELS, blksiz=BLKSIZ, subsample=SUBSAMPLE, device=local) as hq:
+        for _ in range(2):
+            hq.reset()
+            hq.sweep_pcm((q.data_ptr(), frames, np.int16))
+        n_q = 3
+        t0 = time.perf_counter()
+        for _ in range(n_q):
+            hq.reset()
+            hq.sweep_pcm((q.data_ptr(), frames, np.int16))
+            hq.peaks()
+        dt = (time.perf_counter() - t0) / n_q
+        out["e2e_pcm16"] = {"value": float(frames) * CHANNELS * 180 * SUBSAMPLE / dt / 1e9, "unit": "Gsample-angles/s", "ms_per_step": 1e3 * dt,
+                            "h2d_bytes_per_step": int(q.numel() * 2),
+                            "workload": "the headline sweep from a 16-bit PCM image in pinned host memory (phaserot_sweep_pcm): integers over PCIe, widened on the device"}
+    del q
     # -- true-peak sweep (4x), same 1800-angle grid, 10 min stereo device resident
     tf = min(frames, 600 * SR)
     tf -= tf % (32768 - BLKSIZ)

@@ -130,6 +130,20 @@ PHASEROT_API int phaserot_set_stream (phaserot_t* h, void* cuda_stream);
 PHASEROT_API int phaserot_sweep (phaserot_t* h, const float* interleaved, uint64_t n_frames,
                                  int ang_start, int ang_end, int ang_stride, int chn);
 
+/* The same pass over integer PCM as it sits in the file: `pcm` is HOST memory,
+ * interleaved, PHASEROT_PCM_S16 (int16_t) or PHASEROT_PCM_S32 (int32_t; 24-bit
+ * samples left-justified, as sf_readf_int delivers them).  The samples cross
+ * PCIe as integers and are widened on the device with the conversion
+ * libsndfile applies inside sf_readf_float (sample / 2^15, / 2^31), which is
+ * what the reference reads with (cli/phase-rotate.cc:573): the result is
+ * bit-identical to phaserot_sweep() on the converted floats, at half (or the
+ * same) the host traffic.  Replaces sf_readf_float + de-interleave of
+ * analyze_file / thr_process (cli:573, 397-401) for PCM files. */
+#define PHASEROT_PCM_S16 1
+#define PHASEROT_PCM_S32 2
+PHASEROT_API int phaserot_sweep_pcm (phaserot_t* h, const void* pcm, int format, uint64_t n_frames,
+                                     int ang_start, int ang_end, int ang_stride, int chn);
+
 /* Same pass over audio that is already resident in device memory
  * (interleaved, n_frames * n_channels floats).  Work is enqueued on the
  * handle's stream; the peak table is brought back by the next

@@ -16,11 +16,12 @@ E_INVAL, E_NO_DEVICE, E_CUDA, E_NOMEM, E_UNSUPPORTED, E_STATE = -1, -2, -3, -4, 
 MODE_CLI, MODE_PLUGIN = 0, 1
 FLAG_NO_FIRST_BLOCK_QUIRK = 1
 FLAG_NO_PRUNE = 2
+PCM_S16, PCM_S32 = 1, 2
 ABI_VERSION = 3
 
 SYMBOLS = [
     "phaserot_create", "phaserot_destroy", "phaserot_reset", "phaserot_set_stream",
-    "phaserot_sweep", "phaserot_sweep_device", "phaserot_analyze", "phaserot_peak", "phaserot_peaks", "phaserot_lut",
+    "phaserot_sweep", "phaserot_sweep_pcm", "phaserot_sweep_device", "phaserot_analyze", "phaserot_peak", "phaserot_peaks", "phaserot_lut",
     "phaserot_apply", "phaserot_render", "phaserot_render_device",
     "phaserot_process", "phaserot_latency",
     "phaserot_sweep_shard_device", "phaserot_shard_align", "phaserot_pending_table", "phaserot_set_profiling", "phaserot_get_kernel_times",
@@ -80,6 +81,7 @@ def load():
     lib.phaserot_reset.argtypes = [vp]
     lib.phaserot_set_stream.argtypes = [vp, vp]
     lib.phaserot_sweep.argtypes = [vp, vp, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.phaserot_sweep_pcm.argtypes = [vp, vp, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.phaserot_sweep_device.argtypes = [vp, vp, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.phaserot_analyze.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.phaserot_peak.argtypes = [vp, C.c_int, C.c_int]
@@ -172,6 +174,19 @@ class Phaserot:
             x = np.ascontiguousarray(x, np.float32).reshape(-1, self.n_channels)
             ptr, n = x.ctypes.data, x.shape[0]
         self._ck(self._lib.phaserot_sweep(self._h, C.c_void_p(ptr), n, ang_start, ang_end, stride, chn), "phaserot_sweep")
+
+    def sweep_pcm(self, pcm, ang_start=0, ang_end=None, stride=1, chn=-1):
+        """pcm: int16 / int32 array [frames, channels], or (host pointer, n_frames, numpy dtype)."""
+        if ang_end is None:
+            ang_end = self.maxsample
+        if isinstance(pcm, tuple):
+            ptr, n_frames, dt = C.c_void_p(pcm[0]), pcm[1], np.dtype(pcm[2])
+        else:
+            pcm = np.ascontiguousarray(pcm)
+            assert pcm.size % self.n_channels == 0
+            ptr, n_frames, dt = _ptr(pcm), pcm.size // self.n_channels, pcm.dtype
+        fmt = {np.dtype(np.int16): PCM_S16, np.dtype(np.int32): PCM_S32}[dt]
+        self._ck(self._lib.phaserot_sweep_pcm(self._h, ptr, fmt, n_frames, ang_start, ang_end, stride, chn), "phaserot_sweep_pcm")
 
     def sweep_device(self, dev_ptr, n_frames, ang_start=0, ang_end=None, stride=1, chn=-1):
         if ang_end is None:

@@ -669,6 +669,31 @@ __global__ void deinterleave_kernel (const float* __restrict__ in, long long fra
 	}
 }
 
+// Integer PCM -> float on the device, the conversion libsndfile applies in
+// sf_readf_float (what the reference reads with, cli/phase-rotate.cc:573):
+// 16-bit sample / 2^15; 32-bit container (24-bit samples left-justified, as
+// sf_readf_int delivers them) / 2^31.  Both are exact scalings of an exactly
+// (16/24-bit) or correctly rounded (32-bit) converted integer, i.e. bit-identical
+// to the host conversion.  The file then crosses PCIe at 2 (or 4) bytes per
+// sample and is widened at HBM speed.  n = samples (frames * channels).
+template <class I>
+__global__ void __launch_bounds__ (256) pcm_to_float_kernel (const I* __restrict__ in, float* __restrict__ out, long long n)
+{
+	constexpr float   scale = sizeof (I) == 2 ? 1.f / 32768.f : 1.f / 2147483648.f;
+	const long long   i4    = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+	if (i4 + 3 < n && (reinterpret_cast<uintptr_t> (in + i4) & (4 * sizeof (I) - 1)) == 0 && (reinterpret_cast<uintptr_t> (out + i4) & 15) == 0) {
+		I v[4];
+		if (sizeof (I) == 2) {
+			*reinterpret_cast<uint2*> (v) = __ldcs (reinterpret_cast<const uint2*> (in + i4));
+		} else {
+			*reinterpret_cast<uint4*> (v) = __ldcs (reinterpret_cast<const uint4*> (in + i4));
+		}
+		*reinterpret_cast<float4*> (out + i4) = make_float4 ((float)v[0] * scale, (float)v[1] * scale, (float)v[2] * scale, (float)v[3] * scale);
+		return;
+	}
+	for (long long i = i4; i < n && i < i4 + 4; ++i) out[i] = (float)in[i] * scale;
+}
+
 // planes of float2 (two consecutive samples) -> interleaved frames
 __global__ void interleave_kernel (const float2* __restrict__ plane, long long plane_stride, int C,
                                    long long n_count, float* __restrict__ out, long long n_frames_out)

@@ -583,7 +583,7 @@ angle_schedule (phaserot* h, int ang_start, int ang_end, int ang_stride, std::ve
  */
 int
 sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frames, long long t_end, bool first_block,
-            const float* hist, int ang_start, int ang_end, int ang_stride, int chn)
+            const float* hist, int ang_start, int ang_end, int ang_stride, int chn, int pcm_bytes = 0 /* host src is int16 (2) / int32 (4) PCM */)
 {
 	if (chn >= h->C) {
 		return PHASEROT_E_INVAL;
@@ -854,13 +854,23 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 		p.inter = (const float*)h->d_inter.p;
 		rc      = tp_head ();
 		if (rc) return rc;
-		const long long chunk_frames = std::max<long long> (2, ((8LL << 20) / h->C) & ~1LL); // ~32 MB per chunk
+		const long long chunk_frames = std::max<long long> (2, ((8LL << 20) / h->C) & ~1LL); // ~32 MB of floats per chunk
+		const size_t    bps          = pcm_bytes ? (size_t)pcm_bytes : sizeof (float);      // bytes per sample on the host side
 		cudaPointerAttributes at;
 		const bool pinned = (cudaPointerGetAttributes (&at, src) == cudaSuccess) && (at.type == cudaMemoryTypeHost);
 		cudaGetLastError ();
 		if (!pinned) {
 			for (int b = 0; b < 2; ++b) {
-				rc = h->h_stage[b].ensure (sizeof (float) * (size_t)chunk_frames * h->C);
+				rc = h->h_stage[b].ensure (bps * (size_t)chunk_frames * h->C);
+				if (rc) return rc;
+			}
+		}
+		if (pcm_bytes) {
+			// integer PCM: raw chunk -> device staging -> pcm_to_float_kernel on the copy
+			// stream -> the float copy of the file; staging buffer b is reused two chunks
+			// later on the same stream, i.e. after the kernel that read it
+			for (int b = 0; b < 2; ++b) {
+				rc = h->d_stage[b].ensure (bps * (size_t)chunk_frames * h->C);
 				if (rc) return rc;
 			}
 		}
@@ -872,16 +882,30 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 		bool      used[2] = { false, false };
 		while (f0 < n_frames) {
 			const long long nf    = std::min (chunk_frames, n_frames - f0);
-			const size_t    bytes = sizeof (float) * (size_t)nf * h->C;
-			const float*    hsrc  = src + (size_t)f0 * h->C;
+			const size_t    bytes = bps * (size_t)nf * h->C;
+			const void*     hsrc  = (const char*)src + bps * (size_t)f0 * h->C;
 			if (!pinned) {
 				if (used[b]) {
 					CK (cudaEventSynchronize (h->ev_copy[b])); // staging buffer free again
 				}
 				memcpy (h->h_stage[b].p, hsrc, bytes);
-				hsrc = (const float*)h->h_stage[b].p;
+				hsrc = h->h_stage[b].p;
 			}
-			CK (cudaMemcpyAsync ((float*)h->d_inter.p + (size_t)f0 * h->C, hsrc, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+			float* d_chunk = (float*)h->d_inter.p + (size_t)f0 * h->C;
+			if (pcm_bytes) {
+				CK (cudaMemcpyAsync (h->d_stage[b].p, hsrc, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+				const long long ns = nf * h->C;
+				const unsigned  nb = (unsigned)((ns + 1023) / 1024);
+				if (pcm_bytes == 2) {
+					pcm_to_float_kernel<int16_t><<<nb, 256, 0, h->copy_stream>>> ((const int16_t*)h->d_stage[b].p, d_chunk, ns);
+				} else {
+					pcm_to_float_kernel<int32_t><<<nb, 256, 0, h->copy_stream>>> ((const int32_t*)h->d_stage[b].p, d_chunk, ns);
+				}
+				CK (cudaGetLastError ());
+				++h->stats.kernel_launches;
+			} else {
+				CK (cudaMemcpyAsync (d_chunk, hsrc, bytes, cudaMemcpyHostToDevice, h->copy_stream));
+			}
 			CK (cudaEventRecord (h->ev_copy[b], h->copy_stream));
 			CK (cudaStreamWaitEvent (h->stream, h->ev_copy[b], 0));
 			h->stats.h2d_bytes += bytes;
@@ -1348,6 +1372,23 @@ phaserot_sweep (phaserot_t* h, const float* interleaved, uint64_t n_frames, int 
 	const long long B = (F + h->L - 1) / h->L;
 	// analyze_file: B real blocks + one zero flush block (cli:572-586)
 	int rc = sweep_core (h, interleaved, false, F, (B + 1) * h->L, B > 0, nullptr, ang_start, ang_end, ang_stride, chn);
+	if (rc) return rc;
+	return finish_pending (h);
+}
+
+int
+phaserot_sweep_pcm (phaserot_t* h, const void* pcm, int format, uint64_t n_frames, int ang_start, int ang_end, int ang_stride, int chn)
+{
+	if (!h || (!pcm && n_frames) || (format != PHASEROT_PCM_S16 && format != PHASEROT_PCM_S32)) {
+		return PHASEROT_E_INVAL;
+	}
+	if (h->plugin) {
+		return PHASEROT_E_STATE;
+	}
+	DevGuard        guard (h->dev);
+	const long long F = (long long)n_frames;
+	const long long B = (F + h->L - 1) / h->L;
+	int rc = sweep_core (h, (const float*)pcm, false, F, (B + 1) * h->L, B > 0, nullptr, ang_start, ang_end, ang_stride, chn, format == PHASEROT_PCM_S16 ? 2 : 4);
 	if (rc) return rc;
 	return finish_pending (h);
 }

@@ -333,11 +333,20 @@ main (int argc, char** argv)
 		fprintf (vfd, "Process block-size %d\n", blksiz);
 	}
 
-	// the whole file in page-locked memory
-	const uint64_t frames = nfo.frames > 0 ? (uint64_t)nfo.frames : 0;
-	const size_t   fbytes = std::max<size_t> (sizeof (float) * (size_t)frames * (size_t)C, 16);
-	float*         audio  = (float*)phaserot_alloc_host (fbytes);
-	bool           pinned = audio != nullptr;
+	// the whole file in page-locked memory.  Analysis only of an integer PCM file:
+	// the samples stay integers on the host and on the bus (2 bytes per sample for
+	// 16 bit) and are widened on the device exactly as sf_readf_float would
+	// (phaserot_sweep_pcm); everything else is read as float like the reference
+	// does (cli:573).
+	const uint64_t frames  = nfo.frames > 0 ? (uint64_t)nfo.frames : 0;
+	const int      subfmt  = nfo.format & SF_FORMAT_SUBMASK;
+	const int      pcm_fmt = (find_min && !opt.out_path && subfmt == SF_FORMAT_PCM_16)                                 ? PHASEROT_PCM_S16
+	                         : (find_min && !opt.out_path && (subfmt == SF_FORMAT_PCM_24 || subfmt == SF_FORMAT_PCM_32)) ? PHASEROT_PCM_S32
+	                                                                                                                      : 0;
+	const size_t   ssize   = pcm_fmt == PHASEROT_PCM_S16 ? sizeof (short) : sizeof (float); // int and float are both 4 bytes
+	const size_t   fbytes  = std::max<size_t> (ssize * (size_t)frames * (size_t)C, 16);
+	float*         audio   = (float*)phaserot_alloc_host (fbytes);
+	bool           pinned  = audio != nullptr;
 	if (!audio) {
 		audio = (float*)malloc (fbytes);
 	}
@@ -346,7 +355,15 @@ main (int argc, char** argv)
 	}
 	uint64_t got = 0;
 	while (got < frames) {
-		const sf_count_t n = sf_readf_float (infile, audio + got * (uint64_t)C, (sf_count_t)std::min<uint64_t> (frames - got, 1u << 20));
+		const sf_count_t want = (sf_count_t)std::min<uint64_t> (frames - got, 1u << 20);
+		sf_count_t       n;
+		if (pcm_fmt == PHASEROT_PCM_S16) {
+			n = sf_readf_short (infile, (short*)audio + got * (uint64_t)C, want);
+		} else if (pcm_fmt == PHASEROT_PCM_S32) {
+			n = sf_readf_int (infile, (int*)audio + got * (uint64_t)C, want);
+		} else {
+			n = sf_readf_float (infile, audio + got * (uint64_t)C, want);
+		}
 		if (n <= 0) {
 			break;
 		}
@@ -372,7 +389,11 @@ main (int argc, char** argv)
 			fprintf (vfd, "Analyzing using %d process threads, stride = %d\n", C, stride);
 		}
 		// one pass, every grid index (index 0 = raw peak, cli:413-414)
-		check (phaserot_sweep (pr, audio, F, 0, kMaxSample, 1, -1), "analysis failed");
+		if (pcm_fmt) {
+			check (phaserot_sweep_pcm (pr, audio, pcm_fmt, F, 0, kMaxSample, 1, -1), "analysis failed");
+		} else {
+			check (phaserot_sweep (pr, audio, F, 0, kMaxSample, 1, -1), "analysis failed");
+		}
 		PeakTable tab;
 		tab.channels = C;
 		tab.t.resize ((size_t)C * kMaxSample);

@@ -302,6 +302,55 @@ sf_readf_float (SNDFILE* s, float* ptr, sf_count_t frames)
 	return frames;
 }
 
+/* Integer reads of integer PCM files (libsndfile: no scaling, narrower samples are
+ * left-justified in the wider type).  Other sources are outside this subset. */
+static sf_count_t
+read_pcm (SNDFILE* s, void* ptr, sf_count_t frames, int out_bytes)
+{
+	if (!s || s->mode != SFM_READ || frames <= 0 || s->mem || s->is_float || s->bytes_per_sample > out_bytes) {
+		return 0;
+	}
+	if (s->pos + frames > s->info.frames) {
+		frames = s->info.frames - s->pos;
+	}
+	if (frames <= 0) {
+		return 0;
+	}
+	const size_t   ns = (size_t)frames * s->info.channels;
+	unsigned char* b  = scratch (s, ns * s->bytes_per_sample);
+	if (!b) {
+		return 0;
+	}
+	const size_t got = fread (b, s->bytes_per_sample, ns, s->fp);
+	frames           = (sf_count_t)(got / s->info.channels);
+	const size_t n   = (size_t)frames * s->info.channels;
+	for (size_t i = 0; i < n; ++i) {
+		uint32_t v = 0; /* left-justified in 32 bits */
+		for (int k = 0; k < s->bytes_per_sample; ++k) {
+			v |= (uint32_t)b[s->bytes_per_sample * i + k] << (8 * (4 - s->bytes_per_sample + k));
+		}
+		if (out_bytes == 2) {
+			((int16_t*)ptr)[i] = (int16_t)(v >> 16);
+		} else {
+			((int32_t*)ptr)[i] = (int32_t)v;
+		}
+	}
+	s->pos += frames;
+	return frames;
+}
+
+sf_count_t
+sf_readf_short (SNDFILE* s, short* ptr, sf_count_t frames)
+{
+	return read_pcm (s, ptr, frames, 2);
+}
+
+sf_count_t
+sf_readf_int (SNDFILE* s, int* ptr, sf_count_t frames)
+{
+	return read_pcm (s, ptr, frames, 4);
+}
+
 static int32_t
 clip_scale (float v, double scale, double maxv)
 {

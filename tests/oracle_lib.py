@@ -227,6 +227,25 @@ def write_wav_f32(path, x, sr):
         f.write(data)
 
 
+def write_wav_pcm(path, q, sr, bits):
+    """q: integer samples [frames, channels] (int16 for 16 bit; int32 holding 24-bit or 32-bit values)."""
+    import struct
+    q = np.asarray(q)
+    if q.ndim == 1:
+        q = q[:, None]
+    n, c = q.shape
+    if bits == 16:
+        data = q.astype("<i2").tobytes()
+    elif bits == 24:
+        b = q.astype("<i4").reshape(-1).view(np.uint8).reshape(-1, 4)[:, :3]
+        data = np.ascontiguousarray(b).tobytes()
+    else:
+        data = q.astype("<i4").tobytes()
+    with open(path, "wb") as f:
+        f.write(b"RIFF" + struct.pack("<I", 36 + len(data)) + b"WAVEfmt " + struct.pack("<IHHIIHH", 16, 1, c, sr, sr * c * bits // 8, c * bits // 8, bits) + b"data" + struct.pack("<I", len(data)))
+        f.write(data)
+
+
 def read_wav_f32(path):
     import struct
     b = open(path, "rb").read()

@@ -540,6 +540,59 @@ def test_cli_search_output_matches_reference_text(golden, tmp_path):
                 assert np.allclose(fa, fb, atol=2e-4), (a, b)
 
 
+def test_sweep_pcm_is_bit_identical_to_float_sweep():
+    """phaserot_sweep_pcm: int16 / int32 PCM widened on the device gives the table of
+    phaserot_sweep on the floats libsndfile would deliver (sample / 2^15, / 2^31), bit for bit; ragged
+    length (not a multiple of 4 samples) and a pinned source included."""
+    rng = np.random.default_rng(5)
+    x = O.programme(48000, 3.0, 2)[:143999]
+    q16 = np.clip(np.round(x * 32768.0), -32768, 32767).astype(np.int16)
+    q24 = (np.clip(np.round(x * 8388608.0), -8388608, 8388607).astype(np.int32)) << 8      # left-justified 24 bit
+    q32 = rng.integers(-2**31, 2**31 - 1, size=x.shape, dtype=np.int64).astype(np.int32) >> 2  # needs rounding to float
+    with capi.Phaserot(n_channels=2, blksiz=8192) as h:
+        for q, scale in [(q16, 1.0 / 32768.0), (q24, 1.0 / 2147483648.0), (q32, 1.0 / 2147483648.0)]:
+            xf = (q.astype(np.float32) * np.float32(scale)).astype(np.float32)
+            h.reset()
+            h.sweep(xf)
+            ref = h.peaks()
+            h.reset()
+            h.sweep_pcm(q)
+            assert np.array_equal(h.peaks(), ref), q.dtype
+        # pinned source: the chunks go out without the staging copy
+        import ctypes
+        lib = capi.load()
+        p = lib.phaserot_alloc_host(q16.nbytes)
+        ctypes.memmove(p, q16.ctypes.data, q16.nbytes)
+        h.reset()
+        h.sweep_pcm((p, q16.shape[0], np.int16))
+        got = h.peaks()
+        lib.phaserot_free_host(p)
+        h.reset()
+        h.sweep((q16.astype(np.float32) / np.float32(32768.0)).astype(np.float32))
+        assert np.array_equal(got, h.peaks())
+        st = h.stats()
+    assert st["h2d_bytes"] > 0
+    with pytest.raises(capi.PhaserotError):
+        with capi.Phaserot(n_channels=2, blksiz=8192) as h:
+            h._ck(h._lib.phaserot_sweep_pcm(h._h, q16.ctypes.data, 7, 10, 0, 360, 1, -1), "bad format")
+
+
+def test_cli_on_pcm_files_matches_float_file(tmp_path):
+    """The CLI keeps 16/24-bit PCM files integer up to the device (analysis only); its report equals
+    the one for the float file holding the same sample values."""
+    x = O.two_sine(48000, 2.0, 2)
+    q16 = np.clip(np.round(x * 32768.0), -32768, 32767).astype(np.int16)
+    q24 = np.clip(np.round(x * 8388608.0), -8388608, 8388607).astype(np.int32)
+    for bits, q, scale in [(16, q16, 32768.0), (24, q24, 8388608.0)]:
+        wf, wp = str(tmp_path / f"f{bits}.wav"), str(tmp_path / f"p{bits}.wav")
+        O.write_wav_f32(wf, (q.astype(np.float64) / scale).astype(np.float32), 48000)
+        O.write_wav_pcm(wp, q, 48000, bits)
+        for argv in ([], ["-s", "1"], ["-vv", "-s", "12"]):
+            a, b = _cli(*argv, wf), _cli(*argv, wp)
+            assert a.returncode == 0 and b.returncode == 0, (a.stderr, b.stderr)
+            assert a.stdout == b.stdout, (bits, argv)
+
+
 def test_cli_render_matches_reference_files(golden, tmp_path):
     g = golden["cli_render"]
     L = int(g["blksiz"])
