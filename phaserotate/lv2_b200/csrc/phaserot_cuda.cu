@@ -455,6 +455,8 @@ init_front_pad (phaserot* h, const float* hist_frames)
 // bootstrap gate of the digital sweep: keep points with r^2 >= kBootBeta * (largest r^2 seen), i.e. r >= 0.8 r_max
 constexpr float kBootBeta = 0.64f;
 
+inline bool OS_is_digital (const phaserot* h) { return h->OS <= 1; }
+
 struct SweepCfg {
 	int nt, R, gy;
 };
@@ -639,8 +641,13 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 
 	// survivor list: one launch covers at most `segs_max` segments per channel
 	const int       nchan    = c1 - c0;
-	const long long segs_max = std::max<long long> (1, ((long long)h->n_sm * 8) / nchan);
-	const long long segs_cap = std::min (segs_max, std::max<long long> (nseg, 1));
+	// (8 segments per CTA; device-resident digital-peak input: 32 from the second
+	// contiguous launch on - by then the radius is close to final, a launch leaves a
+	// few dozen survivors, and every launch + sweep saved is ~10 us.  Host input keeps
+	// 8, so that little work is left when the last chunk has landed.)
+	const long long segs_first = std::max<long long> (1, ((long long)h->n_sm * 8) / nchan);
+	const long long segs_max   = (src_is_device && OS_is_digital (h)) ? 4 * segs_first : segs_first;
+	const long long segs_cap   = std::min (segs_max, std::max<long long> (nseg, 1));
 	const int       OS       = h->OS;
 	h->list_stride           = segs_cap * h->V * 2 * (OS > 1 ? OS + 1 : 1); // true-peak: the sample and OS interpolated points
 	rc                       = h->d_list.ensure ((size_t)h->list_stride * h->C * sizeof (float2));
@@ -699,6 +706,7 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 	long long       seg_done     = 0;
 	const long long wave     = std::max<long long> (1, (h->n_sm + nchan - 1) / nchan); // segments per channel in one wave
 	bool            booted   = thr_mode != 1;
+	int             n_main   = 0; // contiguous launches so far
 
 	TpParams tp;
 	memset (&tp, 0, sizeof (tp));
@@ -826,7 +834,7 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 			booted = true;
 		}
 		while (seg_done < seg_ready) {
-			const long long want = booted ? segs_max : wave;
+			const long long want = !booted ? wave : (n_main == 0 ? segs_first : segs_max);
 			const long long n    = std::min (want, seg_ready - seg_done);
 			if (!final && n < want && seg_ready < nseg) {
 				break; // wait for more data to keep launches full
@@ -835,6 +843,7 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 			if (r) return r;
 			seg_done += n;
 			booted = true;
+			++n_main;
 		}
 		return PHASEROT_OK;
 	};
