@@ -98,14 +98,74 @@ def gen_numpy(n_frames, seed=43):
 # ---------------------------------------------------------------------------
 
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region.  NVML in-process (a step is ~1.4 ms, the
+    timed region some 15 ms: nvidia-smi's loop mode does not even start that fast), sampled every
+    0.5 ms on a thread; nvidia-smi -lms as the fallback when pynvml is not importable."""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap", 0x80: "hw_power_brake_slowdown"}
 
     def __init__(self, gpu_index):
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.nvml = None
+        self.samples = []
+        self.stop_flag = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                import torch
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(gpu_index).uuid)
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid)
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        n = self.nvml
+        while not self.stop_flag:
+            try:
+                sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                try:
+                    rs = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                except Exception:
+                    rs = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                self.samples.append((sm, rs))
+            except Exception:
+                break
+            time.sleep(0.0005)
 
     def start(self):
+        if self.nvml is not None:
+            self.stop_flag = False
+            self.thr = threading.Thread(target=self._poll, daemon=True)
+            self.thr.start()
+            return
+        self._start_smi()
+
+    def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thr.join(timeout=2)
+            n = self.nvml
+            try:
+                mx = float(n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM))
+            except Exception:
+                mx = None
+            sm = [float(a) for a, _ in self.samples]
+            reasons = set()
+            for _, rs in self.samples:
+                for bit, nm in self.BITS.items():
+                    if rs & bit:
+                        reasons.add(nm)
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "samples": len(sm), "reasons": sorted(reasons),
+                    "source": "nvml, 0.5 ms period, timed region only"}
+        return self._stop_smi()
+
+    def _start_smi(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -118,7 +178,7 @@ class ClockSampler:
         for ln in self.proc.stdout:
             self.lines.append(ln.strip())
 
-    def stop(self):
+    def _stop_smi(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
         time.sleep(0.15)
