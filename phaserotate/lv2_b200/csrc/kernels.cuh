@@ -415,6 +415,7 @@ __device__ __forceinline__ void epilogue (const float2 (&w)[32], float* xch, uin
 				if (ok[kk]) {
 					float2          y  = make_float2 (pv, w[k].x);
 					const long long t0 = 2 * (cx.mbase + i);
+					if (EPI == EPI_HILBERT) cx.rawmax = fmaxf (cx.rawmax, fmaxf (fabsf (pv), fabsf (w[k].x))); // bootstrap gate of the true-peak sweep
 					if (EPI == EPI_RENDER) {
 						float2 cs0 = cs, cs1 = cs;
 						if (t0 < rlen) {
@@ -639,6 +640,12 @@ __global__ void __launch_bounds__ (kConvThreads, 1) fftconv_kernel (const ConvPa
 		float r = cx.rawmax;
 		for (int o = 16; o; o >>= 1) r = fmaxf (r, __shfl_xor_sync (0xffffffffu, r, o));
 		if (lane == 0) atomicMax (p.rawpeak + c, __float_as_uint (r));
+	}
+	if (EPI == EPI_HILBERT && p.r2max && s_begin < s_end) {
+		// largest H^2 of the launch: truepeak_kernel gates its bootstrap wave on it
+		float r = cx.rawmax;
+		for (int o = 16; o; o >>= 1) r = fmaxf (r, __shfl_xor_sync (0xffffffffu, r, o));
+		if (lane == 0) atomicMax (p.r2max + c, __float_as_uint (r * r));
 	}
 	tmem_free_all (tmem, tid);
 }
@@ -911,6 +918,9 @@ struct TpParams {
 	long long    h_stride;
 	int          chan0;
 	long long    seg0, seg_stride;
+	int          seg_jitter;  // same pseudo-random segment offsets as ConvParams::seg_jitter
+	float        boot_beta;   // > 0: bootstrap wave, additionally gate on boot_beta * r2max[c]
+	const unsigned* r2max;    // [channel] float bits of the largest H^2 of the launch (written by the FFT kernel)
 	int          V2;          // samples per segment (2 V)
 	int          D;           // delay of the direct branch in samples (L / 2)
 	long long    t_skip;      // t <  t_skip : not examined            (first-block rule, cli:418-419)
@@ -939,14 +949,49 @@ __device__ __forceinline__ float tp_interp (const float (&s)[16], int n)
 	return a;
 }
 
-__global__ void __launch_bounds__ (256) truepeak_kernel (const TpParams p)
+// both components of a pair (x_d, H) at once: one FFMA2 per tap, the coefficient
+// broadcast to the two halves as an immediate
+template <int PH>
+__device__ __forceinline__ float2 tp_interp2 (const float2 (&s)[16], int n)
+{
+	float2 a = make_float2 (0.f, 0.f);
+#pragma unroll
+	for (int k = 0; k < 12; ++k) a = __ffma2_rn (make_float2 (tp_coef (PH, k), tp_coef (PH, k)), s[12 + n - k], a);
+	return a;
+}
+
+// survivors of one sample (bit q of `keep` = point q) -> list, one atomic per warp
+__device__ __forceinline__ void tp_append (float2* lst, unsigned* cnt, unsigned keep, const float2 (&pt)[5], int lane)
+{
+	if (__any_sync (0xffffffffu, keep != 0)) {
+		// exclusive prefix sum of the per-lane survivor counts
+		const int nk  = __popc (keep);
+		int       inc = nk;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			const int v = __shfl_up_sync (0xffffffffu, inc, o);
+			if (lane >= o) inc += v;
+		}
+		unsigned base = 0;
+		if (lane == 31) base = atomicAdd (cnt, (unsigned)inc);
+		base          = __shfl_sync (0xffffffffu, base, 31);
+		unsigned pos  = base + (unsigned)(inc - nk);
+#pragma unroll
+		for (int q = 0; q < 5; ++q) {
+			if (keep & (1u << q)) lst[pos++] = pt[q];
+		}
+	}
+}
+
+__global__ void __launch_bounds__ (256, 4) truepeak_kernel (const TpParams p)
 {
 	__shared__ __align__ (16) float sh[kTpTile + kTpHalo], sx[kTpTile + kTpHalo], sq[kTpTile + kTpHalo];
 	const int       c    = p.chan0 + blockIdx.y;
 	const int       tps  = p.V2 / kTpTile; // tiles per segment
 	const int       si   = blockIdx.x / tps, tile = blockIdx.x - si * tps;
 	const long long u0   = (long long)si * p.V2 + (long long)tile * kTpTile;                        // launch-compact index
-	const long long t0   = (p.seg0 + si * p.seg_stride) * (long long)p.V2 + (long long)tile * kTpTile; // stream time
+	const long long seg  = p.seg0 + si * p.seg_stride + (p.seg_jitter ? (long long)(((unsigned)si * 2654435761u >> 8) % (unsigned)p.seg_stride) : 0);
+	const long long t0   = seg * (long long)p.V2 + (long long)tile * kTpTile; // stream time
 	if (t0 >= p.t_end) return;
 	// the 11 samples of H before the tile: inside the segment, in the previous
 	// segment of a contiguous launch, or in the carry of the previous launch; a
@@ -955,6 +1000,62 @@ __global__ void __launch_bounds__ (256) truepeak_kernel (const TpParams p)
 	const bool   head_ok = p.seg_stride == 1 || tile > 0;
 	const float* Hc      = p.H + (long long)c * p.h_stride + kTpCarry + u0 - kTpHalo;
 	const bool   q1      = t0 - kTpHalo < p.t_zero; // tile touches the forced-zero region of the direct branch
+	// Interior tile (nearly all of them): every sample exists, is examined, has its
+	// direct branch inside the input and no forced zeros.  The pairs (x_d, H) go
+	// to shared memory as float2 and every interpolation is a packed FFMA2 chain.
+	if (!q1 && head_ok && t0 - kTpHalo >= p.t_skip && t0 + kTpTile <= p.t_end && t0 - kTpHalo - p.D >= 0 && t0 + kTpTile - p.D <= p.n_frames) {
+		__shared__ __align__ (16) float2 sp[kTpTile + kTpHalo];
+		const float* xc = p.inter + (t0 - kTpHalo - p.D) * p.C + c;
+#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			const int i = threadIdx.x + 256 * j;
+			sp[i]       = make_float2 (__ldg (xc + (long long)i * p.C), __ldg (Hc + i));
+		}
+		if (threadIdx.x < kTpHalo) {
+			const int i = kTpTile + threadIdx.x;
+			sp[i]       = make_float2 (__ldg (xc + (long long)i * p.C), __ldg (Hc + i));
+		}
+		__syncthreads ();
+		float2 w[16];
+		{
+			const float4* s4 = reinterpret_cast<const float4*> (sp) + 2 * threadIdx.x;
+#pragma unroll
+			for (int v = 0; v < 8; ++v) {
+				const float4 a = s4[v];
+				w[2 * v]     = make_float2 (a.x, a.y);
+				w[2 * v + 1] = make_float2 (a.z, a.w);
+			}
+		}
+		float          thr2f = p.thr2[c];
+		if (p.boot_beta > 0.f) thr2f = fmaxf (thr2f, p.boot_beta * __uint_as_float (p.r2max[c]));
+		float2*        lstf  = p.list + (long long)c * p.list_stride;
+		unsigned*      cntf  = p.count + c;
+		const int      lanef = threadIdx.x & 31;
+		float          rmax  = 0.f;
+#pragma unroll
+		for (int n = 0; n < 4; ++n) {
+			float2 pt[5];
+			pt[0] = w[12 + n];
+			pt[1] = tp_interp2<0> (w, n);
+			pt[3] = tp_interp2<2> (w, n);
+			if (p.os == 4) {
+				pt[2] = tp_interp2<1> (w, n);
+				pt[4] = tp_interp2<3> (w, n);
+			} else {
+				pt[2] = pt[4] = make_float2 (0.f, 0.f);
+			}
+			unsigned keep = 0;
+#pragma unroll
+			for (int q = 0; q < 5; ++q) {
+				rmax = fmaxf (rmax, fabsf (pt[q].x));
+				if (fmaf (pt[q].x, pt[q].x, pt[q].y * pt[q].y) >= thr2f && (p.os == 4 || !(q == 2 || q == 4))) keep |= 1u << q;
+			}
+			tp_append (lstf, cntf, keep, pt, lanef);
+		}
+		for (int o = 16; o; o >>= 1) rmax = fmaxf (rmax, __shfl_xor_sync (0xffffffffu, rmax, o));
+		if (lanef == 0 && rmax > 0.f) atomicMax (p.rawpeak + c, __float_as_uint (rmax));
+		return;
+	}
 	for (int i = threadIdx.x; i < kTpTile + kTpHalo; i += blockDim.x) {
 		const long long t = t0 - kTpHalo + i;
 		const float     x = tp_input_at (p, c, t - p.D);
@@ -983,7 +1084,8 @@ __global__ void __launch_bounds__ (256) truepeak_kernel (const TpParams p)
 			}
 		}
 	}
-	const float    thr2 = p.thr2[c];
+	float          thr2 = p.thr2[c];
+	if (p.boot_beta > 0.f) thr2 = fmaxf (thr2, p.boot_beta * __uint_as_float (p.r2max[c])); // any subset is valid in the bootstrap
 	float2*        lst  = p.list + (long long)c * p.list_stride;
 	unsigned*      cnt  = p.count + c;
 	const int      lane = threadIdx.x & 31;
@@ -1016,24 +1118,7 @@ __global__ void __launch_bounds__ (256) truepeak_kernel (const TpParams p)
 			if (in) rawmax = fmaxf (rawmax, fabsf (xr[q]));
 			if (ex && fmaf (pt[q].x, pt[q].x, pt[q].y * pt[q].y) >= thr2 && (p.os == 4 || !(q == 2 || q == 4))) keep |= 1u << q;
 		}
-		if (__any_sync (0xffffffffu, keep != 0)) {
-			// one atomic per warp: exclusive prefix sum of the per-lane survivor counts
-			const int nk  = __popc (keep);
-			int       inc = nk;
-#pragma unroll
-			for (int o = 1; o < 32; o <<= 1) {
-				const int v = __shfl_up_sync (0xffffffffu, inc, o);
-				if (lane >= o) inc += v;
-			}
-			unsigned base = 0;
-			if (lane == 31) base = atomicAdd (cnt, (unsigned)inc);
-			base          = __shfl_sync (0xffffffffu, base, 31);
-			unsigned pos  = base + (unsigned)(inc - nk);
-#pragma unroll
-			for (int q = 0; q < 5; ++q) {
-				if (keep & (1u << q)) lst[pos++] = pt[q];
-			}
-		}
+		tp_append (lst, cnt, keep, pt, lane);
 	}
 	for (int o = 16; o; o >>= 1) rawmax = fmaxf (rawmax, __shfl_xor_sync (0xffffffffu, rawmax, o));
 	if (lane == 0 && rawmax > 0.f) atomicMax (p.rawpeak + c, __float_as_uint (rawmax));

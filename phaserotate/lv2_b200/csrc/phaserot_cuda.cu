@@ -646,7 +646,7 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 	// few dozen survivors, and every launch + sweep saved is ~10 us.  Host input keeps
 	// 8, so that little work is left when the last chunk has landed.)
 	const long long segs_first = std::max<long long> (1, ((long long)h->n_sm * 8) / nchan);
-	const long long segs_max   = (src_is_device && OS_is_digital (h)) ? 4 * segs_first : segs_first;
+	const long long segs_max   = !src_is_device ? segs_first : (OS_is_digital (h) ? 4 : 2) * segs_first; // true-peak: the list holds OS + 1 points per sample
 	const long long segs_cap   = std::min (segs_max, std::max<long long> (nseg, 1));
 	const int       OS       = h->OS;
 	h->list_stride           = segs_cap * h->V * 2 * (OS > 1 ? OS + 1 : 1); // true-peak: the sample and OS interpolated points
@@ -732,6 +732,7 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 		tp.count       = p.count;
 		tp.thr2        = p.thr2;
 		tp.rawpeak     = p.rawpeak;
+		tp.r2max       = d_r2max (h);
 	}
 	// true-peak: Hilbert branch of the launch -> staging, carry of the last samples to the next launch
 	auto tp_carry = [&] (long long n) -> int {
@@ -749,11 +750,15 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 		p.nseg       = n;
 		int r;
 		if (OS > 1) {
+			p.seg_jitter = boot && stride > 1;
+			p.r2max      = boot ? d_r2max (h) : nullptr;
 			r = launch_conv<EPI_HILBERT, SRC_INTER> (h, p);
 			if (r) return r;
 			tp.inter      = p.inter;
 			tp.seg0       = s0;
 			tp.seg_stride = stride;
+			tp.seg_jitter = p.seg_jitter;
+			tp.boot_beta  = boot ? kBootBeta : 0.f;
 			{
 				ProfScope  ps (h, 6);
 				const dim3 grid ((unsigned)(n * (tp.V2 / kTpTile)), (unsigned)nchan);
@@ -818,18 +823,10 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 			// which only the strongest points (squared radius within kBootBeta of the
 			// largest one the launch has seen) are swept - a few hundred well-spread
 			// strong points already put every angle's running peak close to its
-			// final value.  True-peak: a handful of segments with everything kept,
-			// then one wave.  The main passes below visit these segments again,
-			// which is harmless for a running maximum.
-			int r;
-			if (OS > 1) {
-				const long long n1 = std::max<long long> (1, 8 / nchan);
-				r = run_launch (seg_ready / (2 * n1), seg_ready / n1, n1);
-				if (r) return r;
-				r = run_launch (0, seg_ready / wave, wave);
-			} else {
-				r = run_launch (0, seg_ready / wave, wave, true);
-			}
+			// final value.  True-peak: the same wave, gated on the largest H^2 the
+			// FFT kernel saw in it.  The main passes below visit these segments
+			// again, which is harmless for a running maximum.
+			const int r = run_launch (0, seg_ready / wave, wave, true);
 			if (r) return r;
 			booted = true;
 		}
