@@ -641,12 +641,14 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 
 	// survivor list: one launch covers at most `segs_max` segments per channel
 	const int       nchan    = c1 - c0;
-	// (8 segments per CTA; device-resident digital-peak input: 32 from the second
-	// contiguous launch on - by then the radius is close to final, a launch leaves a
-	// few dozen survivors, and every launch + sweep saved is ~10 us.  Host input keeps
-	// 8, so that little work is left when the last chunk has landed.)
+	// (8 segments per CTA; device-resident digital-peak input: up to 128 from the
+	// second contiguous launch on - by then the radius is close to final, a launch
+	// leaves a few dozen survivors, and every launch + sweep saved is ~20 us: an hour
+	// of stereo is bootstrap + 2 launches.  The list is sized by the stream, at most
+	// 3.7 GB.  Host input keeps 8, so that little work is left when the last chunk
+	// has landed.)
 	const long long segs_first = std::max<long long> (1, ((long long)h->n_sm * 8) / nchan);
-	const long long segs_max   = !src_is_device ? segs_first : (OS_is_digital (h) ? 4 : 2) * segs_first; // true-peak: the list holds OS + 1 points per sample
+	const long long segs_max   = !src_is_device ? segs_first : (OS_is_digital (h) ? 16 : 2) * segs_first; // true-peak: the list holds OS + 1 points per sample
 	const long long segs_cap   = std::min (segs_max, std::max<long long> (nseg, 1));
 	const int       OS       = h->OS;
 	h->list_stride           = segs_cap * h->V * 2 * (OS > 1 ? OS + 1 : 1); // true-peak: the sample and OS interpolated points

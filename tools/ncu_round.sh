@@ -8,8 +8,8 @@ mkdir -p gpurun_out
 K='regex:fftconv_kernel|sweep_kernel|threshold_kernel|truepeak_kernel|tp_carry|interleave_kernel|fir_stream'
 ncu --metrics gpu__time_duration.sum --clock-control none -k "$K" -c 400 --csv \
     --log-file gpurun_out/ncu_${TAG}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-extra > gpurun_out/ncu_${TAG}_bench_under_ncu.log 2>&1
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k 'regex:fftconv_kernel' -s 10 -c 10 --csv \
+ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k 'regex:fftconv_kernel' -s 6 -c 6 --csv \
     --log-file gpurun_out/ncu_${TAG}_traffic.csv python tools/prof_sweep.py --seconds 3600 --steps 4 > gpurun_out/ncu_${TAG}_traffic.log 2>&1
-ncu --set full --clock-control none --import-source on -k 'regex:fftconv_kernel' -s 7 -c 1 -o gpurun_out/ncu_${TAG}_conv -f \
+ncu --set full --clock-control none --import-source on -k 'regex:fftconv_kernel' -s 5 -c 1 -o gpurun_out/ncu_${TAG}_conv -f \
     python tools/prof_sweep.py --seconds 3600 --steps 2 > gpurun_out/ncu_${TAG}_full.log 2>&1
 ls -la gpurun_out | tail -8
