@@ -25,7 +25,7 @@ out = {
     "launches_per_step": per_step,
     "launches_captured": len(ids),
     "source": f"{os.path.relpath(path, ROOT)}: dram__bytes_read.sum + dram__bytes_write.sum of the fftconv_kernel<EPI_POINTS> launches of "
-              f"{len(ids) // per_step} whole sweep step(s) ({per_step} launches per step: bootstrap wave, 8 and 32 segments per CTA, remainder), "
+              f"{len(ids) // per_step} whole sweep step(s) ({per_step} launches per step: bootstrap wave, then 8 and up to 128 segments per CTA), "
               "1 h stereo 48 kHz; algorithmic bytes on the same basis = 1382350848 per step",
 }
 json.dump(out, open(os.path.join(ROOT, "profiles", "ncu_traffic.json"), "w"), indent=1)
