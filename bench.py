@@ -412,6 +412,27 @@ def secondary_legs(torch, capi, dev, local, x, frames, hbm_peak):
     return out
 
 
+def bind_to_gpu_numa_node(torch, local):
+    """Run this rank on the CPUs NVML reports as local to its GPU (what `numactl --cpunodebind` does for a
+    production launch), BEFORE any page-locked buffer is allocated: with 8 ranks uploading at once, host
+    buffers that sit on the other socket share the inter-socket link and the end-to-end rate of those
+    ranks drops to a third.  Returns the CPU list, or None when nothing was changed."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        uuid = "GPU-" + str(torch.cuda.get_device_properties(local).uuid)
+        h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid)
+        ncpu = os.cpu_count() or 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {i for i in range(ncpu) if (mask[i // 64] >> (i % 64)) & 1} & set(os.sched_getaffinity(0))
+        if cpus and cpus != set(os.sched_getaffinity(0)):
+            os.sched_setaffinity(0, cpus)
+            return sorted(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def gpu_main(args):
     import torch
     import torch.distributed as dist
@@ -424,6 +445,7 @@ def gpu_main(args):
         raise RuntimeError("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa = bind_to_gpu_numa_node(torch, local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -585,6 +607,7 @@ def gpu_main(args):
             "config": workload_config(args),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": "Gsample-angles/s", "h2d_bytes_per_step": int(frames * CHANNELS * 4 * world),
+                    "host_numa_binding": ("rank bound to %d GPU-local CPUs" % len(numa)) if numa else "none",
                     "d2h_bytes_per_step": int((CHANNELS * A + CHANNELS) * 4 * world), "steps": e2e_steps,
                     "ms_per_step": 1e3 * float(t_e2e.item()) / e2e_steps},
             "gpu_launches": int(launches.item()),
