@@ -234,6 +234,17 @@ PHASEROT_API int phaserot_render_device (phaserot_t* h, const float* d_interleav
 PHASEROT_API int phaserot_process (phaserot_t* h, const float* const* in, float* const* out,
                                    uint32_t n_frames, const float* angle_deg);
 
+/* phaserot_process() that also returns the two level-meter inputs of the
+ * plugin's run() for this call, reduced on the device: level_in[c] = max |x|
+ * over the input delayed by the plugin latency (the samples that line up with
+ * this call's output; src/phaserotate.c:573-609), level_out[c] = max |y| over
+ * the n_frames outputs (src:727-739).  NaNs are ignored (fmax).  Either pointer
+ * NULL = plain phaserot_process().  The meter ballistics (hold, fall-off,
+ * peak-hold, `levels` notification) stay on the host: they are per call, not
+ * per sample. */
+PHASEROT_API int phaserot_process_levels (phaserot_t* h, const float* const* in, float* const* out, uint32_t n_frames,
+                                          const float* angle_deg, float* level_in, float* level_out);
+
 /* Replaces: FFTiProc::latency = parsiz + firlat (src:297); CLI: blksiz / 2 (cli:963). */
 PHASEROT_API uint32_t phaserot_latency (const phaserot_t* h);
 

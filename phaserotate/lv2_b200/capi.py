@@ -23,7 +23,7 @@ SYMBOLS = [
     "phaserot_create", "phaserot_destroy", "phaserot_reset", "phaserot_set_stream",
     "phaserot_sweep", "phaserot_sweep_pcm", "phaserot_sweep_device", "phaserot_analyze", "phaserot_peak", "phaserot_peaks", "phaserot_lut",
     "phaserot_apply", "phaserot_render", "phaserot_render_device",
-    "phaserot_process", "phaserot_latency",
+    "phaserot_process", "phaserot_process_levels", "phaserot_latency",
     "phaserot_sweep_shard_device", "phaserot_shard_align", "phaserot_pending_table", "phaserot_set_profiling", "phaserot_get_kernel_times",
     "phaserot_sync", "phaserot_get_stats", "phaserot_reset_stats",
     "phaserot_alloc_host", "phaserot_free_host",
@@ -92,6 +92,7 @@ def load():
     lib.phaserot_render.argtypes = [vp, vp, C.c_uint64, vp, C.c_int, vp]
     lib.phaserot_render_device.argtypes = [vp, vp, C.c_uint64, vp, C.c_int, vp]
     lib.phaserot_process.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.c_uint32, vp]
+    lib.phaserot_process_levels.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.c_uint32, vp, vp, vp]
     lib.phaserot_latency.argtypes = [vp]
     lib.phaserot_latency.restype = C.c_uint32
     lib.phaserot_sweep_shard_device.argtypes = [vp, vp, C.c_uint64, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
@@ -277,6 +278,19 @@ class Phaserot:
         ang = np.ascontiguousarray(np.broadcast_to(np.asarray(angle_deg, np.float32), (self.n_channels,)))
         self._ck(self._lib.phaserot_process(self._h, ins, outs, n, _ptr(ang)), "phaserot_process")
         return out
+
+    def process_levels(self, x_planar, angle_deg):
+        """Like process(); returns (output, level_in[channels], level_out[channels])."""
+        x = np.ascontiguousarray(x_planar, np.float32).reshape(self.n_channels, -1)
+        out = np.zeros_like(x)
+        n = x.shape[1]
+        ins = (C.c_void_p * self.n_channels)(*[x[c].ctypes.data for c in range(self.n_channels)])
+        outs = (C.c_void_p * self.n_channels)(*[out[c].ctypes.data for c in range(self.n_channels)])
+        ang = np.ascontiguousarray(np.broadcast_to(np.asarray(angle_deg, np.float32), (self.n_channels,)))
+        li = np.zeros(self.n_channels, np.float32)
+        lo = np.zeros(self.n_channels, np.float32)
+        self._ck(self._lib.phaserot_process_levels(self._h, ins, outs, n, _ptr(ang), _ptr(li), _ptr(lo)), "phaserot_process_levels")
+        return out, li, lo
 
     def process_raw(self, in_ptrs, out_ptrs, n, ang):
         self._ck(self._lib.phaserot_process(self._h, in_ptrs, out_ptrs, n, _ptr(ang)), "phaserot_process")

@@ -838,7 +838,8 @@ constexpr int kStreamOut = 32;
 
 __global__ void __launch_bounds__ (128) fir_stream_kernel (float* __restrict__ ring, const float* __restrict__ xin, int xin_stride, int n,
                                                             long long t0, int parsiz, const float* __restrict__ g, int nodd, int firlat,
-                                                            const float2* __restrict__ pre, int pre_stride, FirCoef fc, float* __restrict__ yout)
+                                                            const float2* __restrict__ pre, int pre_stride, FirCoef fc, float* __restrict__ yout,
+                                                            float* __restrict__ lev)
 {
 	extern __shared__ float sh[]; // g[nodd] | window[2 nodd + 32] | partial[4][32]
 	const int c  = blockIdx.y;
@@ -875,11 +876,54 @@ __global__ void __launch_bounds__ (128) fir_stream_kernel (float* __restrict__ r
 		sp[q * 32 + o] = (a0 + a1) + (a2 + a3);
 	}
 	__syncthreads ();
-	if (q == 0 && o < nb) {
-		const float  hv = (sp[o] + sp[32 + o]) + (sp[64 + o] + sp[96 + o]);
-		const float  xd = sx[2 * nodd + o - firlat];
-		const float2 cs = (o0 + o) < fc.rlen[c] ? pre[(long long)c * pre_stride + o0 + o] : fc.cs[c];
-		yout[(long long)c * n + o0 + o] = __fadd_rn (__fmul_rn (cs.x, xd), __fmul_rn (cs.y, hv));
+	if (q == 0) { // warp 0
+		float ax = 0.f, ay = 0.f;
+		if (o < nb) {
+			const float  hv = (sp[o] + sp[32 + o]) + (sp[64 + o] + sp[96 + o]);
+			const float  xd = sx[2 * nodd + o - firlat];
+			const float2 cs = (o0 + o) < fc.rlen[c] ? pre[(long long)c * pre_stride + o0 + o] : fc.cs[c];
+			const float  y  = __fadd_rn (__fmul_rn (cs.x, xd), __fmul_rn (cs.y, hv));
+			yout[(long long)c * n + o0 + o] = y;
+			ax = fabsf (xd);
+			ay = fabsf (y);
+		}
+		if (lev) {
+			// level meters of the plugin (src:573-609, 727-739): max |delayed input| and
+			// max |output| of this CTA's 32 samples; the host takes the max over the
+			// CTAs of the call.  fmaxf drops NaNs like the host meter did.
+			for (int s = 16; s; s >>= 1) {
+				ax = fmaxf (ax, __shfl_xor_sync (0xffffffffu, ax, s));
+				ay = fmaxf (ay, __shfl_xor_sync (0xffffffffu, ay, s));
+			}
+			if (o == 0) {
+				float* l = lev + 2 * ((long long)c * gridDim.x + blockIdx.x);
+				l[0]     = ax;
+				l[1]     = ay;
+			}
+		}
+	}
+}
+
+// max |a[i]| and max |b[i]|, i < n, per channel (blockIdx.y) -> lev[c][0], lev[c][1]
+// (float bits, atomicMax; values >= 0).  Bulk plugin calls: a = delayed input, b = output.
+__global__ void __launch_bounds__ (256) absmax2_kernel (const float* __restrict__ a, long long a_stride, const float* __restrict__ b, long long b_stride,
+                                                         long long n, unsigned* __restrict__ lev)
+{
+	const int    c  = blockIdx.y;
+	const float* pa = a + (long long)c * a_stride;
+	const float* pb = b + (long long)c * b_stride;
+	float        ma = 0.f, mb = 0.f;
+	for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+		ma = fmaxf (ma, fabsf (pa[i]));
+		mb = fmaxf (mb, fabsf (pb[i]));
+	}
+	for (int s = 16; s; s >>= 1) {
+		ma = fmaxf (ma, __shfl_xor_sync (0xffffffffu, ma, s));
+		mb = fmaxf (mb, __shfl_xor_sync (0xffffffffu, mb, s));
+	}
+	if ((threadIdx.x & 31) == 0) {
+		atomicMax (lev + 2 * c, __float_as_uint (ma));
+		atomicMax (lev + 2 * c + 1, __float_as_uint (mb));
 	}
 }
 

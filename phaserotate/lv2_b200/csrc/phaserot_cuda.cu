@@ -1693,13 +1693,22 @@ phaserot_latency (const phaserot_t* h)
 int
 phaserot_process (phaserot_t* h, const float* const* in, float* const* out, uint32_t n_frames, const float* angle_deg)
 {
+	return phaserot_process_levels (h, in, out, n_frames, angle_deg, nullptr, nullptr);
+}
+
+int
+phaserot_process_levels (phaserot_t* h, const float* const* in, float* const* out, uint32_t n_frames, const float* angle_deg,
+                         float* level_in, float* level_out)
+{
 	if (!h || !in || !out || !angle_deg) {
 		return PHASEROT_E_INVAL;
 	}
 	if (!h->plugin) {
 		return PHASEROT_E_STATE;
 	}
+	const bool want_levels = level_in && level_out;
 	if (n_frames == 0) {
+		for (int c = 0; want_levels && c < h->C; ++c) level_in[c] = level_out[c] = 0.f;
 		return PHASEROT_OK;
 	}
 	DevGuard       guard (h->dev);
@@ -1718,12 +1727,14 @@ phaserot_process (phaserot_t* h, const float* const* in, float* const* out, uint
 	const uint32_t n_comp   = (uint32_t)((t0 + n) / P) - first_np; // partitions completing in this call
 	const size_t   pre_cap  = (size_t)P * 20;                      // a full 180 degree ramp is <= 9 partitions (src:295)
 	const bool     small    = n <= 16384;
-	const size_t   io_bytes = sizeof (float) * wstride * C + sizeof (float2) * pre_cap * C + (small ? sizeof (float) * (size_t)n * C : 0) + 64;
+	const size_t   n_cta    = (n + kStreamOut - 1) / kStreamOut; // CTAs per channel of the small-call kernel
+	const size_t   io_bytes = sizeof (float) * wstride * C + sizeof (float2) * pre_cap * C + (small ? sizeof (float) * ((size_t)n + 2 * n_cta) * C : 0) + 64;
 	int            rc       = h->h_io.ensure (io_bytes);
 	if (rc) return rc;
 	float*  W    = (float*)h->h_io.p;
 	float2* pre  = (float2*)(W + wstride * C);
 	float*  yout = (float*)(pre + pre_cap * C);
+	float*  lev  = yout + (size_t)n * C; // small calls: [C][n_cta][2] per-CTA (max |delayed input|, max |output|)
 
 	float2 chan_cs[2];
 	int    ramp_len[2] = { 0, 0 };
@@ -1807,6 +1818,7 @@ phaserot_process (phaserot_t* h, const float* const* in, float* const* out, uint
 		const float*  dW    = (const float*)dbase;
 		const float2* dpre  = (const float2*)(dbase + ((const char*)pre - (const char*)h->h_io.p));
 		float*        dy    = (float*)(dbase + ((const char*)yout - (const char*)h->h_io.p));
+		float*        dlev  = want_levels ? (float*)(dbase + ((const char*)lev - (const char*)h->h_io.p)) : nullptr;
 		FirCoef       fc;
 		for (int c = 0; c < 2; ++c) {
 			fc.cs[c]   = chan_cs[c < C ? c : 0];
@@ -1816,13 +1828,22 @@ phaserot_process (phaserot_t* h, const float* const* in, float* const* out, uint
 		{
 			ProfScope ps (h, 4);
 			fir_stream_kernel<<<grid, 128, smem, h->stream>>> ((float*)h->d_ring.p, dW + keep, (int)wstride, (int)n, (long long)t0, (int)P,
-			                                                    (const float*)h->d_g.p, nodd, (int)h->firlat, dpre, (int)pre_cap, fc, dy);
+			                                                    (const float*)h->d_g.p, nodd, (int)h->firlat, dpre, (int)pre_cap, fc, dy, dlev);
 		}
 		CK (cudaGetLastError ());
 		++h->stats.kernel_launches;
 		CK (cudaStreamSynchronize (h->stream));
 		for (int c = 0; c < C; ++c) {
 			memcpy (out[c], yout + (size_t)c * n, sizeof (float) * n);
+			if (want_levels) {
+				float li = 0.f, lo = 0.f;
+				for (size_t b = 0; b < n_cta; ++b) { // 32 values per 1024-frame call
+					li = std::fmax (li, lev[2 * ((size_t)c * n_cta + b)]);
+					lo = std::fmax (lo, lev[2 * ((size_t)c * n_cta + b) + 1]);
+				}
+				level_in[c]  = li;
+				level_out[c] = lo;
+			}
 		}
 		h->stats.h2d_bytes += sizeof (float) * (size_t)n * C;
 		h->stats.d2h_bytes += sizeof (float) * (size_t)n * C;
@@ -1896,7 +1917,24 @@ phaserot_process (phaserot_t* h, const float* const* in, float* const* out, uint
 			const float* src = (const float*)((float2*)h->d_out.p + (long long)c * h->out_stride) + firlen;
 			CK (cudaMemcpyAsync (out[c], src, sizeof (float) * n, cudaMemcpyDeviceToHost, h->stream));
 		}
+		unsigned levbits[4] = { 0, 0, 0, 0 };
+		if (want_levels) {
+			// level meters: the delayed input of output i is W index firlen - firlat + i (plane, float view)
+			unsigned* dl = (unsigned*)d_thr2 (h); // [C][2] scratch in the small-state buffer (unused in plugin mode)
+			CK (cudaMemsetAsync (dl, 0, sizeof (unsigned) * 2 * (size_t)C, h->stream));
+			const float* xa = (const float*)((float2*)h->d_plane.p + h->padf) + (firlen - h->firlat);
+			const float* ya = (const float*)h->d_out.p + firlen;
+			const dim3   grid ((unsigned)std::min<size_t> (((size_t)n + 255) / 256, (size_t)h->n_sm * 4), (unsigned)C);
+			absmax2_kernel<<<grid, 256, 0, h->stream>>> (xa, 2 * h->plane_stride, ya, 2 * h->out_stride, (long long)n, dl);
+			CK (cudaGetLastError ());
+			++h->stats.kernel_launches;
+			CK (cudaMemcpyAsync (levbits, dl, sizeof (unsigned) * 2 * (size_t)C, cudaMemcpyDeviceToHost, h->stream));
+		}
 		CK (cudaStreamSynchronize (h->stream));
+		for (int c = 0; want_levels && c < C; ++c) {
+			memcpy (&level_in[c], &levbits[2 * c], sizeof (float));
+			memcpy (&level_out[c], &levbits[2 * c + 1], sizeof (float));
+		}
 		h->stats.d2h_bytes += sizeof (float) * (size_t)n * C;
 	}
 	return PHASEROT_OK;

@@ -8,8 +8,9 @@
 // reported latency.  lv2ttl/*.in of the reference describe this binary as is.
 //
 // What moved to the GPU is the audio path of process_channel()
-// (src/phaserotate.c:615-721): one phaserot_process() call per run().  The level
-// meters stay on the host; they only look at the port buffers.
+// (src/phaserotate.c:615-721): one phaserot_process_levels() call per run(), which
+// also returns the per-call maxima of the delayed input and of the output,
+// reduced on the device; only the meter ballistics (per call) stay on the host.
 // No CPU DSP fallback: if the CUDA backend cannot be created, instantiate()
 // returns NULL like the reference does on any allocation failure (src:315-372).
 #include <cmath>
@@ -113,21 +114,11 @@ struct Meter {
 	}
 };
 
-float
-abs_max (const float* d, uint32_t n, float m = 0.f)
-{
-	for (uint32_t i = 0; i < n; ++i) {
-		m = std::fmax (m, std::fabs (d[i]));
-	}
-	return m;
-}
-
 struct ChannelState {
 	float* in    = nullptr;
 	float* out   = nullptr;
 	float* angle = nullptr;
 
-	std::vector<float> delayed; // last `latency` input samples, oldest first (input meter runs on the delayed signal)
 	Meter              m_in, m_out;
 	float              diff_min = 1, diff_max = 1;
 	int                reset_delay = 0;
@@ -267,9 +258,6 @@ instantiate (const LV2_Descriptor* descriptor, double rate, const char*, const L
 		return nullptr;
 	}
 	p->latency = phaserot_latency (p->dsp);
-	for (uint32_t c = 0; c < p->n_chn; ++c) {
-		p->ch[c].delayed.assign (p->latency, 0.f);
-	}
 	return (LV2_Handle)p;
 }
 
@@ -302,27 +290,7 @@ activate (LV2_Handle instance)
 	for (uint32_t c = 0; c < p->n_chn; ++c) {
 		p->ch[c].reset_meters ();
 		p->ch[c].reset_delay = (int)p->latency;
-		std::fill (p->ch[c].delayed.begin (), p->ch[c].delayed.end (), 0.f);
 	}
-}
-
-// input level of this period, measured `latency` samples late so that it lines
-// up with the output (src:573-609); keeps the delay line up to date
-float
-delayed_input_level (Plugin* p, ChannelState& ch, const float* in, uint32_t n)
-{
-	const uint32_t lat = p->latency;
-	float          lvl;
-	if (n < lat) {
-		lvl = abs_max (ch.delayed.data (), n);
-		memmove (ch.delayed.data (), ch.delayed.data () + n, sizeof (float) * (lat - n));
-		memcpy (ch.delayed.data () + (lat - n), in, sizeof (float) * n);
-	} else {
-		lvl = abs_max (ch.delayed.data (), lat);
-		lvl = abs_max (in, n - lat, lvl);
-		memcpy (ch.delayed.data (), in + (n - lat), sizeof (float) * lat);
-	}
-	return ch.m_in.feed (lvl, p->hold_frames, p->period, p->falloff);
 }
 
 void
@@ -393,7 +361,6 @@ run (LV2_Handle instance, uint32_t n_samples)
 		angles[c]        = *ch.angle;
 		ins[c]           = ch.out; // processed in place on the output buffer like the reference (src:563)
 		outs[c]          = ch.out;
-		lvl_in[c]        = delayed_input_level (p, ch, ch.out, n_samples);
 		// meter_delayed_reset (src:497-509, 611): after an angle change the
 		// output/diff meters restart once the new setting has reached the output
 		float target = std::fmin (0.5f, std::fmax (-0.5f, angles[c] / -360.f));
@@ -407,7 +374,9 @@ run (LV2_Handle instance, uint32_t n_samples)
 		}
 		ch.last_target = target;
 	}
-	const int rc = phaserot_process (p->dsp, ins, outs, n_samples, angles);
+	// the input level is measured `latency` samples late so that it lines up with the output (src:573-609)
+	float     lvl_out_raw[kMaxChannels] = { 0, 0 };
+	const int rc = phaserot_process_levels (p->dsp, ins, outs, n_samples, angles, lvl_in, lvl_out_raw);
 	if (rc != PHASEROT_OK) {
 		// real-time context: no way to report; emit silence rather than stale data
 		for (uint32_t c = 0; c < p->n_chn; ++c) {
@@ -424,7 +393,8 @@ run (LV2_Handle instance, uint32_t n_samples)
 	// --- meters + notifications -------------------------------------------
 	for (uint32_t c = 0; c < p->n_chn; ++c) {
 		ChannelState& ch      = p->ch[c];
-		const float   lvl_out = ch.m_out.feed (abs_max (ch.out, n_samples), p->hold_frames, p->period, p->falloff);
+		lvl_in[c]             = ch.m_in.feed (rc == PHASEROT_OK ? lvl_in[c] : 0.f, p->hold_frames, p->period, p->falloff);
+		const float   lvl_out = ch.m_out.feed (rc == PHASEROT_OK ? lvl_out_raw[c] : 0.f, p->hold_frames, p->period, p->falloff);
 		float         diff    = 1.0;
 		if (ch.m_in.momentary > 0.001f && ch.m_out.momentary > 0.001f) {
 			diff        = ch.m_out.momentary / ch.m_in.momentary;

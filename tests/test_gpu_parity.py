@@ -479,6 +479,32 @@ def test_plugin_bulk_and_mixed_call_sizes():
         assert np.max(np.abs(yg[c] - yo)) <= AUDIO_TOL * float(np.abs(yo).max())
 
 
+def test_plugin_levels_reduced_on_device():
+    """phaserot_process_levels: the meter inputs of run() come back from the device -
+    max |input delayed by the latency| and max |output| of each call - for small (streaming kernel) and
+    bulk (FFT path) calls alike; the audio is that of phaserot_process."""
+    rng = np.random.default_rng(11)
+    for nch, sizes in [(1, [1024] * 6 + [100, 7, 333]), (2, [256, 256, 40000, 1024, 20000])]:
+        x = (0.3 * rng.standard_normal((nch, sum(sizes)))).astype(np.float32)
+        x[0, 1500] = np.nan                      # the meters ignore NaNs (fmax)
+        with capi.Phaserot(mode=capi.MODE_PLUGIN, n_channels=nch, sample_rate=48000.0) as h, \
+             capi.Phaserot(mode=capi.MODE_PLUGIN, n_channels=nch, sample_rate=48000.0) as h2:
+            lat = h.latency()
+            xd = np.concatenate([np.zeros((nch, lat), np.float32), x], 1)   # delayed input: xd[:, t] = x[:, t - lat]
+            pos = 0
+            for n in sizes:
+                y, li, lo = h.process_levels(x[:, pos:pos + n], 33.0)
+                y2 = h2.process(x[:, pos:pos + n], 33.0)
+                assert np.array_equal(y, y2, equal_nan=True)
+                for c in range(nch):
+                    want_in = np.nanmax(np.abs(xd[c, pos:pos + n]), initial=0.0)
+                    yy = np.abs(y[c])
+                    want_out = np.nanmax(yy, initial=0.0) if np.isfinite(yy).any() else 0.0
+                    assert li[c] == np.float32(want_in), (nch, pos, n, c)
+                    assert lo[c] == np.float32(want_out), (nch, pos, n, c)
+                pos += n
+
+
 def test_plugin_golden_reference_vectors(golden):
     g = golden["plugin"]
     for rate, blk in [(48000, 256), (48000, 1000), (96000, 1024), (192000, 2048)]:
