@@ -203,3 +203,22 @@ def test_oracle_vs_reference_render_and_plugin(oracle_built):
         yr, lat, _ = O.lv2_render(so, xm, 48000, blk, ang[:, None])
         assert lat == 1792
         assert np.max(np.abs(O.oracle_plugin_run(xm, 48000, blk, ang) - yr[0])) < TOL
+
+
+@needs_ref
+def test_reference_cli_reads_pcm_files_like_float_files(oracle_built, tmp_path):
+    """The stand-in libsndfile converts 16/24/32-bit PCM the way libsndfile does (sample / 2^15, / 2^31),
+    so the unmodified reference CLI reports the same angles for a PCM file and for the float file
+    holding the same sample values - the property phaserot_sweep_pcm is tested against on the GPU."""
+    import subprocess
+    x = O.two_sine(48000, 0.5, 2)
+    exe = os.path.join(O.REF_DIR, "phase-rotate")
+    for bits, scale in [(16, 32768.0), (24, 8388608.0), (32, 2147483648.0)]:
+        q = np.clip(np.round(x.astype(np.float64) * scale), -scale, scale - 1).astype(np.int64)
+        wf, wp = str(tmp_path / f"f{bits}.wav"), str(tmp_path / f"p{bits}.wav")
+        O.write_wav_f32(wf, (q.astype(np.float64) / scale).astype(np.float32), 48000)
+        O.write_wav_pcm(wp, q.astype(np.int32) if bits > 16 else q.astype(np.int16), 48000, bits)
+        a = subprocess.run([exe, "-f", "1024", "-s", "4", wf], capture_output=True, text=True)
+        b = subprocess.run([exe, "-f", "1024", "-s", "4", wp], capture_output=True, text=True)
+        assert a.returncode == 0 and b.returncode == 0, (a.stderr, b.stderr)
+        assert a.stdout == b.stdout and "Phase" in a.stdout, bits
