@@ -262,6 +262,43 @@ def test_pending_table_on_device_and_device_history():
         assert np.array_equal(h.peaks(), whole)
 
 
+def test_multichannel_paths_agree():
+    """Four interleaved channels: host input (chunked upload), device input and two shards (host and
+    device history) all give the table of the oracle / of one another; pruned == brute force bit for bit."""
+    import torch
+    x = O.programme(48000, 4.0, 2)
+    x4 = np.ascontiguousarray(np.stack([x[:, 0], x[:, 1], 0.7 * x[::-1, 0], 0.5 * (x[:, 0] - x[:, 1])], 1).astype(np.float32))
+    L = 8192
+    frames = x4.shape[0] - x4.shape[0] % L
+    x4 = x4[:frames]
+    po = O.oracle_analyze(x4, L)
+    xd = torch.from_numpy(x4).cuda()
+    with capi.Phaserot(n_channels=4, blksiz=L) as h:
+        h.sweep(x4)
+        host = h.peaks()
+        h.reset()
+        h.sweep_device(xd.data_ptr(), frames)
+        dev = h.peaks()
+        al = h.shard_align()
+        half = (frames // 2) - ((frames // 2) % al)
+        tabs = []
+        for hist_dev in (False, True):
+            h.reset()
+            h.sweep_shard_device(xd.data_ptr(), half, None, True, False)
+            a = h.peaks()
+            hist = xd[half - L:half].contiguous()
+            h.reset()
+            h.sweep_shard_device(xd[half:].data_ptr(), frames - half, hist.data_ptr() if hist_dev else hist.cpu().numpy(), False, True)
+            tabs.append(np.maximum(a, h.peaks()))
+    with capi.Phaserot(n_channels=4, blksiz=L, flags=capi.FLAG_NO_PRUNE) as h:
+        h.sweep_device(xd.data_ptr(), frames)
+        brute = h.peaks()
+    assert rel(dev, po) <= PEAK_TOL
+    assert np.array_equal(host, dev) and np.array_equal(dev, brute)
+    assert np.array_equal(tabs[0], dev) and np.array_equal(tabs[1], dev)
+    assert np.array_equal(dev.argmin(1), po.argmin(1))
+
+
 def test_blksiz_32768_pruned_equals_brute_force_and_shards_combine():
     """FIR length 32768 (two tap partitions): 2 min stereo at 0.1 deg, same properties as above."""
     L = 32768
