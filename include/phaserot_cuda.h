@@ -32,7 +32,7 @@ extern "C" {
 #define PHASEROT_API __attribute__ ((visibility ("default")))
 #endif
 
-#define PHASEROT_ABI_VERSION 3
+#define PHASEROT_ABI_VERSION 4
 
 typedef struct phaserot phaserot_t;
 
@@ -141,6 +141,12 @@ PHASEROT_API int phaserot_sweep (phaserot_t* h, const float* interleaved, uint64
  * analyze_file / thr_process (cli:573, 397-401) for PCM files. */
 #define PHASEROT_PCM_S16 1
 #define PHASEROT_PCM_S32 2
+/* packed 24-bit little-endian samples exactly as they sit in a WAV / RF64 / W64 data chunk
+ * (what sf_read_raw returns): 3 bytes per sample on the host and on the bus, widened on the
+ * device to the value sf_readf_float delivers (sample / 2^23) */
+#define PHASEROT_PCM_S24 3
+/* interleaved float32 (the format of phaserot_sweep), for the calls below that take a format */
+#define PHASEROT_PCM_F32 0
 PHASEROT_API int phaserot_sweep_pcm (phaserot_t* h, const void* pcm, int format, uint64_t n_frames,
                                      int ang_start, int ang_end, int ang_stride, int chn);
 
@@ -168,7 +174,44 @@ PHASEROT_API int phaserot_sweep_shard_device (phaserot_t* h, const float* d_inte
                                               const float* hist, int first, int last,
                                               int ang_start, int ang_end, int ang_stride, int chn);
 
+/* The same shard from HOST memory (`data`: interleaved, `format` = PHASEROT_PCM_*;
+ * pinned is faster): uploaded in chunks on a copy stream while the compute stream
+ * works on what has landed, like phaserot_sweep().  `hist`: blksiz frames of
+ * float32 history (host or device) or NULL.  Asynchronous like the device form:
+ * the table comes back with the next phaserot_peak()/phaserot_peaks()/phaserot_sync(),
+ * so phaserot_pending_table() can be combined across ranks first.  Replaces the
+ * read loop of analyze_file (cli:565-587) for one rank's part of the file. */
+PHASEROT_API int phaserot_sweep_shard (phaserot_t* h, const void* data, int format, uint64_t n_frames,
+                                       const float* hist, int first, int last,
+                                       int ang_start, int ang_end, int ang_stride, int chn);
+
 PHASEROT_API uint32_t phaserot_shard_align (const phaserot_t* h);
+
+/* ---- several GPUs in one process ---------------------------------------- */
+
+/* A group of handles, one per device, that analyses ONE stream: the file is cut
+ * on phaserot_shard_align() into one contiguous shard per device (sample-range
+ * sharding; every shard reads blksiz frames of history in front), every device
+ * uploads and sweeps its shard concurrently, and the per-angle maxima are
+ * combined on the first device by a kernel that reads the other devices'
+ * tables through NVLink peer memory (element-wise max; exact and associative,
+ * so the result equals the single-device table bit for bit).  No NCCL
+ * bootstrap: a CLI run is over before a communicator would be up.  Replaces
+ * analyze_file + the merge of the per-thread `_peak` rows (cli:431-444,
+ * 565-587) for `phase-rotate --gpus N`.
+ *   devices   : n_devices CUDA ordinals (NULL = 0 .. n_devices - 1); cfg->device is ignored
+ * The group's peak table is read with phaserot_group_peaks(); handle 0 of the
+ * group (phaserot_group_handle) serves render / lut / latency queries. */
+typedef struct phaserot_group phaserot_group_t;
+PHASEROT_API int  phaserot_group_create (phaserot_group_t** out, const phaserot_cfg_t* cfg, const int* devices, int n_devices);
+PHASEROT_API void phaserot_group_destroy (phaserot_group_t* g);
+PHASEROT_API int  phaserot_group_size (const phaserot_group_t* g);
+PHASEROT_API phaserot_t* phaserot_group_handle (phaserot_group_t* g, int i);
+/* one analyze_file() pass over host memory (`format` = PHASEROT_PCM_*), same angle arguments as phaserot_sweep() */
+PHASEROT_API int  phaserot_group_sweep (phaserot_group_t* g, const void* data, int format, uint64_t n_frames,
+                                        int ang_start, int ang_end, int ang_stride, int chn);
+PHASEROT_API int  phaserot_group_peaks (phaserot_group_t* g, float* out);
+PHASEROT_API int  phaserot_group_reset (phaserot_group_t* g);
 
 /* Device-resident result of the sweep that is still pending (enqueued, not read
  * back yet), for combining shards without a host round trip: *d_table points at
@@ -244,6 +287,12 @@ PHASEROT_API int phaserot_process (phaserot_t* h, const float* const* in, float*
  * per sample. */
 PHASEROT_API int phaserot_process_levels (phaserot_t* h, const float* const* in, float* const* out, uint32_t n_frames,
                                           const float* angle_deg, float* level_in, float* level_out);
+
+/* Angle state of every channel in turns (Channel::angle, src/phaserotate.c:53), as
+ * process_channel() finds it at the start of the NEXT call: the reference re-arms
+ * its delayed meter reset while `target_angle != angle` (src:564-571, 611), i.e.
+ * for as long as the ramp is still moving.  angle_turns: [n_channels]. */
+PHASEROT_API int phaserot_plugin_angle (phaserot_t* h, float* angle_turns);
 
 /* Replaces: FFTiProc::latency = parsiz + firlat (src:297); CLI: blksiz / 2 (cli:963). */
 PHASEROT_API uint32_t phaserot_latency (const phaserot_t* h);

@@ -16,15 +16,17 @@ E_INVAL, E_NO_DEVICE, E_CUDA, E_NOMEM, E_UNSUPPORTED, E_STATE = -1, -2, -3, -4, 
 MODE_CLI, MODE_PLUGIN = 0, 1
 FLAG_NO_FIRST_BLOCK_QUIRK = 1
 FLAG_NO_PRUNE = 2
-PCM_S16, PCM_S32 = 1, 2
-ABI_VERSION = 3
+PCM_F32, PCM_S16, PCM_S32, PCM_S24 = 0, 1, 2, 3
+ABI_VERSION = 4
 
 SYMBOLS = [
     "phaserot_create", "phaserot_destroy", "phaserot_reset", "phaserot_set_stream",
     "phaserot_sweep", "phaserot_sweep_pcm", "phaserot_sweep_device", "phaserot_analyze", "phaserot_peak", "phaserot_peaks", "phaserot_lut",
     "phaserot_apply", "phaserot_render", "phaserot_render_device",
     "phaserot_process", "phaserot_process_levels", "phaserot_latency",
-    "phaserot_sweep_shard_device", "phaserot_shard_align", "phaserot_pending_table", "phaserot_set_profiling", "phaserot_get_kernel_times",
+    "phaserot_sweep_shard_device", "phaserot_sweep_shard", "phaserot_shard_align", "phaserot_plugin_angle",
+    "phaserot_group_create", "phaserot_group_destroy", "phaserot_group_size", "phaserot_group_handle", "phaserot_group_sweep",
+    "phaserot_group_peaks", "phaserot_group_reset", "phaserot_pending_table", "phaserot_set_profiling", "phaserot_get_kernel_times",
     "phaserot_sync", "phaserot_get_stats", "phaserot_reset_stats",
     "phaserot_alloc_host", "phaserot_free_host",
     "phaserot_strerror", "phaserot_last_error", "phaserot_abi_version",
@@ -70,7 +72,7 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB
+    path = os.environ.get("PHASEROT_LIB") or _build.LIB  # PHASEROT_LIB: A/B runs of two builds (tools/ab_kernel.sh)
     if not os.path.exists(path):
         _build.build_library()
     lib = C.CDLL(path)
@@ -96,6 +98,17 @@ def load():
     lib.phaserot_latency.argtypes = [vp]
     lib.phaserot_latency.restype = C.c_uint32
     lib.phaserot_sweep_shard_device.argtypes = [vp, vp, C.c_uint64, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.phaserot_sweep_shard.argtypes = [vp, vp, C.c_int, C.c_uint64, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.phaserot_plugin_angle.argtypes = [vp, vp]
+    lib.phaserot_group_create.argtypes = [C.POINTER(vp), C.POINTER(Cfg), vp, C.c_int]
+    lib.phaserot_group_destroy.argtypes = [vp]
+    lib.phaserot_group_destroy.restype = None
+    lib.phaserot_group_size.argtypes = [vp]
+    lib.phaserot_group_handle.argtypes = [vp, C.c_int]
+    lib.phaserot_group_handle.restype = vp
+    lib.phaserot_group_sweep.argtypes = [vp, vp, C.c_int, C.c_uint64, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.phaserot_group_peaks.argtypes = [vp, vp]
+    lib.phaserot_group_reset.argtypes = [vp]
     lib.phaserot_shard_align.argtypes = [vp]
     lib.phaserot_pending_table.argtypes = [vp, C.POINTER(C.POINTER(C.c_float)), C.POINTER(C.c_int), C.POINTER(C.c_int)]
     lib.phaserot_shard_align.restype = C.c_uint32
@@ -186,8 +199,30 @@ class Phaserot:
             pcm = np.ascontiguousarray(pcm)
             assert pcm.size % self.n_channels == 0
             ptr, n_frames, dt = _ptr(pcm), pcm.size // self.n_channels, pcm.dtype
-        fmt = {np.dtype(np.int16): PCM_S16, np.dtype(np.int32): PCM_S32}[dt]
+        fmt = {np.dtype(np.int16): PCM_S16, np.dtype(np.int32): PCM_S32, np.dtype(np.uint8): PCM_S24}[dt]
+        if fmt == PCM_S24 and not isinstance(pcm, tuple):
+            n_frames //= 3  # packed 24-bit: uint8 array of 3 bytes per sample
         self._ck(self._lib.phaserot_sweep_pcm(self._h, ptr, fmt, n_frames, ang_start, ang_end, stride, chn), "phaserot_sweep_pcm")
+
+    def sweep_shard(self, data, n_frames, hist, first, last, fmt=PCM_F32, ang_start=0, ang_end=None, stride=1, chn=-1):
+        """Host-memory shard (phaserot_sweep_shard): data = numpy array or raw host pointer; hist like sweep_shard_device."""
+        if ang_end is None:
+            ang_end = self.maxsample
+        dp = C.c_void_p(data) if isinstance(data, int) else _ptr(data)
+        hp = None
+        if isinstance(hist, int):
+            hp = C.c_void_p(hist)
+        elif hist is not None:
+            hist = np.ascontiguousarray(hist, np.float32)
+            assert hist.size == self.blksiz * self.n_channels
+            hp = _ptr(hist)
+        self._ck(self._lib.phaserot_sweep_shard(self._h, dp, fmt, n_frames, hp, int(first), int(last), ang_start, ang_end, stride, chn),
+                 "phaserot_sweep_shard")
+
+    def plugin_angle(self):
+        out = np.zeros(self.n_channels, np.float32)
+        self._ck(self._lib.phaserot_plugin_angle(self._h, _ptr(out)), "phaserot_plugin_angle")
+        return out
 
     def sweep_device(self, dev_ptr, n_frames, ang_start=0, ang_end=None, stride=1, chn=-1):
         if ang_end is None:
@@ -305,3 +340,66 @@ class Phaserot:
 
     def reset_stats(self):
         self._ck(self._lib.phaserot_reset_stats(self._h), "phaserot_reset_stats")
+
+
+class PhaserotGroup:
+    """One stream analysed by several devices of this process (phaserot_group_*)."""
+
+    def __init__(self, n_devices, devices=None, n_channels=1, blksiz=8192, subsample=2, flags=0, oversample=0):
+        self._lib = load()
+        self._g = C.c_void_p()
+        self.n_channels, self.blksiz, self.subsample = n_channels, blksiz, subsample or 2
+        self.maxsample = 180 * self.subsample
+        cfg = Cfg(ABI_VERSION, MODE_CLI, n_channels, blksiz, 48000.0, subsample, -1, flags, oversample)
+        dv = None
+        if devices is not None:
+            self._dev = np.ascontiguousarray(devices, np.int32)
+            dv = _ptr(self._dev)
+        rc = self._lib.phaserot_group_create(C.byref(self._g), C.byref(cfg), dv, n_devices)
+        if rc != OK:
+            self._g = C.c_void_p()
+            raise PhaserotError(rc, "phaserot_group_create", self._lib.phaserot_strerror(rc).decode() + "; " + self._lib.phaserot_last_error().decode())
+
+    def _ck(self, rc, what):
+        if rc != OK:
+            raise PhaserotError(rc, what, self._lib.phaserot_strerror(rc).decode() + "; " + self._lib.phaserot_last_error().decode())
+
+    def size(self):
+        return int(self._lib.phaserot_group_size(self._g))
+
+    def sweep(self, data, n_frames=None, fmt=PCM_F32, ang_start=0, ang_end=None, stride=1, chn=-1):
+        if ang_end is None:
+            ang_end = self.maxsample
+        if isinstance(data, int):
+            dp = C.c_void_p(data)
+        else:
+            data = np.ascontiguousarray(data)
+            dp = _ptr(data)
+            if n_frames is None:
+                n_frames = data.size // self.n_channels // (3 if fmt == PCM_S24 else 1)
+        self._ck(self._lib.phaserot_group_sweep(self._g, dp, fmt, n_frames, ang_start, ang_end, stride, chn), "phaserot_group_sweep")
+
+    def peaks(self):
+        out = np.zeros((self.n_channels, self.maxsample), np.float32)
+        self._ck(self._lib.phaserot_group_peaks(self._g, _ptr(out)), "phaserot_group_peaks")
+        return out
+
+    def reset(self):
+        self._ck(self._lib.phaserot_group_reset(self._g), "phaserot_group_reset")
+
+    def close(self):
+        if self._g:
+            self._lib.phaserot_group_destroy(self._g)
+            self._g = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

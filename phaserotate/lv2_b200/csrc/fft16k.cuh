@@ -90,6 +90,16 @@ PRK_HD float2 cmulk (float2 a, float wr, float wi)
 PRK_HD float2 cmulk (float2 a, float wr, float wi) { return make_float2 (a.x * wr - a.y * wi, a.y * wr + a.x * wi); }
 #endif
 
+// s * a + c and s * (i a) + c, s a scalar (compile-time constant after unrolling:
+// a 32-bit immediate broadcast to both halves of one FFMA2)
+#if defined(__CUDA_ARCH__)
+PRK_HD float2 cfma (float2 a, float s, float2 c) { return __ffma2_rn (a, make_float2 (s, s), c); }
+PRK_HD float2 cfmai (float2 a, float s, float2 c) { return __ffma2_rn (make_float2 (-a.y, a.x), make_float2 (s, s), c); }
+#else
+PRK_HD float2 cfma (float2 a, float s, float2 c) { return make_float2 (a.x * s + c.x, a.y * s + c.y); }
+PRK_HD float2 cfmai (float2 a, float s, float2 c) { return make_float2 (-a.y * s + c.x, a.x * s + c.y); }
+#endif
+
 // DIR = -1 forward (roots exp(-2 pi i / n)), +1 inverse
 template <int DIR>
 PRK_HD void dft4 (float2& a0, float2& a1, float2& a2, float2& a3)
@@ -125,25 +135,69 @@ PRK_HD float2 mulw32 (float2 a)
 	return cmulk (a, cos32 (mm), (DIR < 0 ? -1.f : 1.f) * sin32 (mm));
 }
 
-// 8-point DFT, natural order in and out
+// Twiddled radix-2 butterfly  p = x + W b,  q = x - W b,  W = exp(DIR 2 pi i m / 32),
+// m a loop constant after unrolling.  A twiddle that is consumed only by such a
+// +/- pair never needs its own complex product (FMUL2 + FFMA2): with
+// W = wr (1 + i t), t = wi / wr,
+//     c = b + t (i b)          one FFMA2
+//     p = x + wr c, q = x - wr c   two FFMA2
+// i.e. three packed instructions where product + two adds take four; when
+// |wi| > |wr| the same with W = i wi (1 + i t), t = -wr / wi, so |t| <= 1 always.
 template <int DIR>
-PRK_HD void dft8 (float2 (&v)[8])
+PRK_HD void bfly_w (float2 x, float2 b, int m, float2& p, float2& q)
+{
+	m &= 31;
+	if (m == 0) {
+		p = cadd (x, b);
+		q = csub (x, b);
+	} else if (m == 16) {
+		p = csub (x, b);
+		q = cadd (x, b);
+	} else if (m == 8 || m == 24) {
+		const bool plus_i = (m == 8) == (DIR > 0); // W = +i
+		p = plus_i ? caddi (x, b) : csubi (x, b);
+		q = plus_i ? csubi (x, b) : caddi (x, b);
+	} else {
+		const float wr = cos32 (m), wi = (DIR < 0 ? -1.f : 1.f) * sin32 (m);
+		if ((wr < 0 ? -wr : wr) >= (wi < 0 ? -wi : wi)) {
+			const float2 c = cfmai (b, wi / wr, b);
+			p              = cfma (c, wr, x);
+			q              = cfma (c, -wr, x);
+		} else {
+			const float2 c = cfmai (b, -wr / wi, b);
+			p              = cfmai (c, wi, x);
+			q              = cfmai (c, -wi, x);
+		}
+	}
+}
+
+// dft4 whose inputs a2, a3 still lack their twiddles exp(DIR 2 pi i m / 32), m = m2, m3
+template <int DIR>
+PRK_HD void dft4_lazy (float2& a0, float2& a1, float2& a2, float2& a3, int m2, int m3)
+{
+	float2 s02, d02, s13, d13;
+	bfly_w<DIR> (a0, a2, m2, s02, d02);
+	bfly_w<DIR> (a1, a3, m3, s13, d13);
+	a0 = cadd (s02, s13);
+	a2 = csub (s02, s13);
+	a1 = DIR < 0 ? csubi (d02, d13) : caddi (d02, d13);
+	a3 = DIR < 0 ? caddi (d02, d13) : csubi (d02, d13);
+}
+
+// 8-point DFT, natural order in and out; inputs v[4 .. 7] still lack the
+// twiddles exp(DIR 2 pi i m / 32), m = m4 .. m7 (0 = none)
+template <int DIR>
+PRK_HD void dft8 (float2 (&v)[8], int m4 = 0, int m5 = 0, int m6 = 0, int m7 = 0)
 {
 	float2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6];
 	float2 o0 = v[1], o1 = v[3], o2 = v[5], o3 = v[7];
-	dft4<DIR> (e0, e1, e2, e3);
-	dft4<DIR> (o0, o1, o2, o3);
-	o1   = mulw32<DIR, 4> (o1);
-	o2   = mulw32<DIR, 8> (o2);
-	o3   = mulw32<DIR, 12> (o3);
+	dft4_lazy<DIR> (e0, e1, e2, e3, m4, m6);
+	dft4_lazy<DIR> (o0, o1, o2, o3, m5, m7);
 	v[0] = cadd (e0, o0);
 	v[4] = csub (e0, o0);
-	v[1] = cadd (e1, o1);
-	v[5] = csub (e1, o1);
-	v[2] = cadd (e2, o2);
-	v[6] = csub (e2, o2);
-	v[3] = cadd (e3, o3);
-	v[7] = csub (e3, o3);
+	bfly_w<DIR> (e1, o1, 4, v[1], v[5]);
+	bfly_w<DIR> (e2, o2, 8, v[2], v[6]);
+	bfly_w<DIR> (e3, o3, 12, v[3], v[7]);
 }
 
 // 16-point DFT, natural order in and out (4 x 4)
@@ -160,19 +214,15 @@ PRK_HD void dft16 (float2 (&u)[16])
 		t[k0][2] = a2;
 		t[k0][3] = a3;
 	}
+	// twiddles W_16^(k0 ql) = W_32^(2 k0 ql): k0 = 1 applied here, k0 = 2, 3 inside the
+	// butterflies that consume them (bfly_w)
 	t[1][1] = mulw32<DIR, 2> (t[1][1]);
 	t[1][2] = mulw32<DIR, 4> (t[1][2]);
 	t[1][3] = mulw32<DIR, 6> (t[1][3]);
-	t[2][1] = mulw32<DIR, 4> (t[2][1]);
-	t[2][2] = mulw32<DIR, 8> (t[2][2]);
-	t[2][3] = mulw32<DIR, 12> (t[2][3]);
-	t[3][1] = mulw32<DIR, 6> (t[3][1]);
-	t[3][2] = mulw32<DIR, 12> (t[3][2]);
-	t[3][3] = mulw32<DIR, 18> (t[3][3]);
 #pragma unroll
 	for (int ql = 0; ql < 4; ++ql) {
 		float2 a0 = t[0][ql], a1 = t[1][ql], a2 = t[2][ql], a3 = t[3][ql];
-		dft4<DIR> (a0, a1, a2, a3); // a[qh] = y[ql + 4 qh]
+		dft4_lazy<DIR> (a0, a1, a2, a3, 4 * ql, 6 * ql); // a[qh] = y[ql + 4 qh]
 		u[ql]      = a0;
 		u[ql + 4]  = a1;
 		u[ql + 8]  = a2;
@@ -199,31 +249,34 @@ PRK_HD float2 mulw32v (float2 a, int m)
 //   "8 x 4" (input n = n0 + 4 n1, output p = p0 + 8 p1)
 //      stage 1, per n0: radix-8 over n1, constant twiddle W_32^(n0 p0)      -> t[p0][n0]
 //      stage 2, per p0: radix-4 over n0                                      -> y[p0 + 8 p1]
-// 216 packed instructions either way.  A pass issues its loads in the order
+// A pass issues its loads in the order
 // stage 1 consumes them and stores each stage-2 group as soon as it exists, so
 // that the butterflies run while the rest of the data is still in flight.
+// The constant twiddles between the two stages are applied in stage 1 only where
+// stage 2 consumes the value as the first operand of a butterfly (k0 < 4, n0 < 2);
+// the others ride on the stage-2 butterflies (bfly_w): 196 packed instructions.
 template <int DIR>
 PRK_HD void bf48_stage1 (float2 (&t)[8][4], int k0, float2 a0, float2 a1, float2 a2, float2 a3)
 {
 	dft4<DIR> (a0, a1, a2, a3);
 	t[k0][0] = a0;
-	t[k0][1] = mulw32v<DIR> (a1, k0);
-	t[k0][2] = mulw32v<DIR> (a2, 2 * k0);
-	t[k0][3] = mulw32v<DIR> (a3, 3 * k0);
+	t[k0][1] = k0 < 4 ? mulw32v<DIR> (a1, k0) : a1;
+	t[k0][2] = k0 < 4 ? mulw32v<DIR> (a2, 2 * k0) : a2;
+	t[k0][3] = k0 < 4 ? mulw32v<DIR> (a3, 3 * k0) : a3;
 }
 template <int DIR>
 PRK_HD void bf48_stage2 (const float2 (&t)[8][4], int ql, float2 (&v)[8])
 {
 #pragma unroll
 	for (int k0 = 0; k0 < 8; ++k0) v[k0] = t[k0][ql];
-	dft8<DIR> (v); // v[qh] = y[ql + 4 qh]
+	dft8<DIR> (v, 4 * ql, 5 * ql, 6 * ql, 7 * ql); // v[qh] = y[ql + 4 qh]
 }
 template <int DIR>
 PRK_HD void bf84_stage1 (float2 (&t)[8][4], int n0, float2 (&v)[8])
 {
 	dft8<DIR> (v); // v[p0]
 #pragma unroll
-	for (int p0 = 0; p0 < 8; ++p0) t[p0][n0] = mulw32v<DIR> (v[p0], n0 * p0);
+	for (int p0 = 0; p0 < 8; ++p0) t[p0][n0] = n0 < 2 ? mulw32v<DIR> (v[p0], n0 * p0) : v[p0];
 }
 template <int DIR>
 PRK_HD void bf84_stage2 (const float2 (&t)[8][4], int p0, float2& y0, float2& y1, float2& y2, float2& y3)
@@ -232,7 +285,7 @@ PRK_HD void bf84_stage2 (const float2 (&t)[8][4], int p0, float2& y0, float2& y1
 	y1 = t[p0][1];
 	y2 = t[p0][2];
 	y3 = t[p0][3];
-	dft4<DIR> (y0, y1, y2, y3); // y[p1] = out[p0 + 8 p1]
+	dft4_lazy<DIR> (y0, y1, y2, y3, 2 * p0, 3 * p0); // y[p1] = out[p0 + 8 p1]
 }
 
 // natural order in and out (used by the microbenchmarks and host tests)

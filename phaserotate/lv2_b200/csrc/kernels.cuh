@@ -99,6 +99,11 @@ struct ConvParams {
 	float*        out_inter;    // EPI_RENDER: interleaved destination [out_frames][C] instead of `out` (fused CLI render)
 	long long     out_frames;
 	int           out_compact;  // EPI_HILBERT: segment j of the launch writes its V outputs at out[8 + j V ..) (true-peak staging)
+	// launched as thread-block clusters of `pair_sync` CTAs = the CTAs that walk the channels of one
+	// stretch of interleaved frames: they meet once per segment (split arrive / wait), so that none
+	// runs more than one segment ahead and every sector of the stretch is fetched from HBM once
+	int           pair_sync;
+	int           prefetch;     // 1: pull the next segment towards L2 while the current one is transformed
 };
 
 // Segment input loaders: z[n0 + idx] for the first forward pass and the direct
@@ -576,6 +581,8 @@ __global__ void __launch_bounds__ (kConvThreads, 1) fftconv_kernel (const ConvPa
 	const int c = p.chan0 + ci;
 	bool prev_inside = false;
 	for (int si = s_begin; si < s_end; ++si) {
+		if (p.pair_sync) asm volatile ("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); // "I have started segment si"
+
 		const long long seg = p.seg0 + si * p.seg_stride + (p.seg_jitter ? (long long)(((unsigned)si * 2654435761u >> 8) % (unsigned)p.seg_stride) : 0);
 		const long long n0  = seg * p.V - p.Lh; // complex stream index of local index 0
 		if (NP == 2 && (si == s_begin || p.seg_stride != 1)) {
@@ -586,7 +593,7 @@ __global__ void __launch_bounds__ (kConvThreads, 1) fftconv_kernel (const ConvPa
 				spectrum_only (sm, xch, p.tw1, p.tw2, p.scratch + (size_t)blockIdx.x * (kM / 2), tid, EdgeLoader { p.inter, p.hist, p.n_frames, 2 * (n0 - p.V), p.C, c, p.hist_frames });
 			}
 		}
-		if (si + 1 < s_end && lane == 0 && (SRC == SRC_PLANE || ci == 0)) {
+		if (p.prefetch && si + 1 < s_end && lane == 0 && (SRC == SRC_PLANE || ci == 0)) {
 			// pull the new part of the next segment towards L2 while this one is
 			// transformed: one bulk prefetch per warp, 16 pieces
 			const long long nn0 = n0 + p.seg_stride * p.V + (p.seg_stride == 1 ? p.Lh : 0);
@@ -634,6 +641,7 @@ __global__ void __launch_bounds__ (kConvThreads, 1) fftconv_kernel (const ConvPa
 				run_segment<EPI, NP> (sm, xch, tb, p, tid, lane, cx, InterNLoader { p.inter + 2 * n0 * p.C + c, p.C }, reuse);
 			}
 		}
+		if (p.pair_sync) asm volatile ("barrier.cluster.wait.aligned;" ::: "memory"); // every sibling has started segment si
 	}
 
 	if (EPI == EPI_POINTS && s_begin < s_end) {
@@ -699,6 +707,46 @@ __global__ void __launch_bounds__ (256) pcm_to_float_kernel (const I* __restrict
 		return;
 	}
 	for (long long i = i4; i < n && i < i4 + 4; ++i) out[i] = (float)in[i] * scale;
+}
+
+// packed 24-bit little-endian PCM (3 bytes per sample, as in the file's data chunk) -> float:
+// the sample left-justified in 32 bits times 2^-31 = sample / 2^23, what sf_readf_float returns.
+// `in` is 4-byte aligned; a thread converts 4 samples = 12 bytes = three aligned words.
+__global__ void __launch_bounds__ (256) pcm24_to_float_kernel (const uint8_t* __restrict__ in, float* __restrict__ out, long long n)
+{
+	constexpr float scale = 1.f / 2147483648.f;
+	const long long i4    = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+	if (i4 + 3 < n && (reinterpret_cast<uintptr_t> (out + i4) & 15) == 0) {
+		const uint32_t* w = reinterpret_cast<const uint32_t*> (in + 3 * i4);
+		const uint32_t  a = __ldcs (w), b = __ldcs (w + 1), c = __ldcs (w + 2);
+		const int       s0 = (int)(a << 8);
+		const int       s1 = (int)(((a >> 24) << 8) | (b << 16));
+		const int       s2 = (int)(((b >> 16) << 8) | (c << 24));
+		const int       s3 = (int)(c & 0xffffff00u);
+		*reinterpret_cast<float4*> (out + i4) = make_float4 ((float)s0 * scale, (float)s1 * scale, (float)s2 * scale, (float)s3 * scale);
+		return;
+	}
+	for (long long i = i4; i < n && i < i4 + 4; ++i) {
+		const uint8_t* q = in + 3 * i;
+		const int      v = (int)(((uint32_t)q[0] << 8) | ((uint32_t)q[1] << 16) | ((uint32_t)q[2] << 24));
+		out[i]           = (float)v * scale;
+	}
+}
+
+// Combine the tables of a device group on its first device: dst[i] = max (dst[i], src_k[i]) over the
+// other devices' tables, read in place through NVLink peer memory (or from a gathered copy when peer
+// access is not available).  The values are bit patterns of non-negative floats: unsigned order = float order.
+struct PeerTabs {
+	const unsigned* p[15];
+	int             n;
+};
+__global__ void __launch_bounds__ (256) peer_max_kernel (unsigned* __restrict__ dst, const PeerTabs src, long long n)
+{
+	const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	unsigned v = dst[i];
+	for (int k = 0; k < src.n; ++k) v = max (v, src.p[k][i]);
+	dst[i] = v;
 }
 
 // planes of float2 (two consecutive samples) -> interleaved frames

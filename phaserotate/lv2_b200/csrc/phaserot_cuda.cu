@@ -18,6 +18,8 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <string>
+#include <thread>
 #include <vector>
 
 #ifndef M_PI
@@ -177,6 +179,7 @@ struct phaserot {
 	phaserot_cfg_t cfg;
 	int            dev   = 0;
 	int            n_sm  = 148;
+	int            pair_sync = 1; // clusters of sibling CTAs on interleaved input (PHASEROT_PAIR_SYNC=0 switches it off)
 	int            C     = 1;
 	int            L     = 0;   // FIR length
 	int            Lh    = 0;   // half taps (odd taps of the FIR)
@@ -365,27 +368,82 @@ fill_conv_common (phaserot* h, ConvParams& p)
 	p.G1           = (const float2*)h->d_G1.p;
 	p.scratch      = (float4*)h->d_scratch.p;
 	p.seg_stride   = 1;
+	p.prefetch     = getenv ("PHASEROT_PREFETCH") ? atoi (getenv ("PHASEROT_PREFETCH")) : 1;
+}
+
+// Function attributes are per device (per context): phaserot_create() sets them
+// for every kernel that needs more than the default 48 KB of dynamic shared
+// memory, once per device, under g_create_lock - never on a launch path (an LV2
+// run() must not take locks, and a second handle on another device of the same
+// process must find its own opt-in).
+template <int EPI, int SRC, int NP>
+int
+set_conv_attr ()
+{
+	CK (cudaFuncSetAttribute (fftconv_kernel<EPI, SRC, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+	if (getenv ("PHASEROT_CARVEOUT")) {
+		CK (cudaFuncSetAttribute (fftconv_kernel<EPI, SRC, NP>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi (getenv ("PHASEROT_CARVEOUT"))));
+	}
+	return PHASEROT_OK;
+}
+
+int
+set_device_attrs (int dev) // caller holds g_create_lock and has made `dev` current
+{
+	static std::vector<char> done;
+	if ((size_t)dev < done.size () && done[(size_t)dev]) {
+		return PHASEROT_OK;
+	}
+	int rc;
+	if ((rc = set_conv_attr<EPI_POINTS, SRC_INTER, 1> ())) return rc;
+	if ((rc = set_conv_attr<EPI_POINTS, SRC_INTER, 2> ())) return rc;
+	if ((rc = set_conv_attr<EPI_RENDER, SRC_INTER, 1> ())) return rc;
+	if ((rc = set_conv_attr<EPI_RENDER, SRC_INTER, 2> ())) return rc;
+	if ((rc = set_conv_attr<EPI_RENDER, SRC_PLANE, 1> ())) return rc;
+	if ((rc = set_conv_attr<EPI_RENDER, SRC_PLANE, 2> ())) return rc;
+	if ((rc = set_conv_attr<EPI_HILBERT, SRC_INTER, 1> ())) return rc;
+	if ((rc = set_conv_attr<EPI_HILBERT, SRC_INTER, 2> ())) return rc;
+	CK (cudaFuncSetAttribute (fir_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+	if (done.size () <= (size_t)dev) done.resize ((size_t)dev + 1, 0);
+	done[(size_t)dev] = 1;
+	return PHASEROT_OK;
 }
 
 template <int EPI, int SRC, int NP>
 int
 launch_conv_np (phaserot* h, const ConvParams& p)
 {
-	static bool attr_done = false; // one flag per template instantiation
-	if (!attr_done) {
-		CK (cudaFuncSetAttribute (fftconv_kernel<EPI, SRC, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-		if (getenv ("PHASEROT_CARVEOUT")) {
-			CK (cudaFuncSetAttribute (fftconv_kernel<EPI, SRC, NP>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi (getenv ("PHASEROT_CARVEOUT"))));
-		}
-		attr_done = true;
-	}
 	const long long total = p.nseg * p.nchan;
 	if (total <= 0) {
 		return PHASEROT_OK;
 	}
 	const int grid = (int)std::min<long long> (total, h->n_sm);
 	ProfScope ps (h, EPI == EPI_POINTS ? 0 : EPI == EPI_HILBERT ? 6 : 3);
-	fftconv_kernel<EPI, SRC, NP><<<grid, kConvThreads, kSmemBytes, h->stream>>> (p);
+	// Interleaved multichannel input: the CTAs of the channels of one stretch (block
+	// index b, b + 1, ... of equal b / nchan) form a thread-block cluster and meet
+	// once per segment, see ConvParams::pair_sync.  All CTAs of a cluster walk
+	// runs of the same length because the grid is a multiple of nchan.
+	const int csz = (SRC == SRC_INTER && h->pair_sync && p.seg_stride == 1 && p.nchan >= 2 && p.nchan <= 8 && grid % p.nchan == 0 && p.nseg * p.nchan >= grid) ? p.nchan : 1;
+	if (csz > 1) {
+		ConvParams pc = p;
+		pc.pair_sync  = csz;
+		cudaLaunchConfig_t  lc;
+		cudaLaunchAttribute at[1];
+		memset (&lc, 0, sizeof (lc));
+		lc.gridDim          = dim3 ((unsigned)grid);
+		lc.blockDim         = dim3 (kConvThreads);
+		lc.dynamicSmemBytes = kSmemBytes;
+		lc.stream           = h->stream;
+		at[0].id               = cudaLaunchAttributeClusterDimension;
+		at[0].val.clusterDim.x = (unsigned)csz;
+		at[0].val.clusterDim.y = 1;
+		at[0].val.clusterDim.z = 1;
+		lc.attrs               = at;
+		lc.numAttrs            = 1;
+		CK (cudaLaunchKernelEx (&lc, fftconv_kernel<EPI, SRC, NP>, pc));
+	} else {
+		fftconv_kernel<EPI, SRC, NP><<<grid, kConvThreads, kSmemBytes, h->stream>>> (p);
+	}
 	CK (cudaGetLastError ());
 	++h->stats.kernel_launches;
 	return PHASEROT_OK;
@@ -513,7 +571,10 @@ finish_pending (phaserot* h)
 		return PHASEROT_OK;
 	}
 	const int    A     = h->pend_A;
-	const size_t bytes = sizeof (unsigned) * ((size_t)A * h->C + (size_t)h->C) + 2 * sizeof (unsigned long long);
+	// [C][A] maxima | [C] raw peaks | pad to 8 bytes | 2 x u64 statistics
+	const size_t n_tab = (size_t)A * h->C + (size_t)h->C;
+	const size_t n_pad = n_tab + (n_tab & 1);
+	const size_t bytes = sizeof (unsigned) * n_pad + 2 * sizeof (unsigned long long);
 	int          rc    = h->h_res.ensure (bytes);
 	if (rc) return rc;
 	unsigned* res = (unsigned*)h->h_res.p;
@@ -522,7 +583,7 @@ finish_pending (phaserot* h)
 	} else {
 		CK (cudaMemcpyAsync (res, d_raw (h), sizeof (unsigned) * (size_t)h->C, cudaMemcpyDeviceToHost, h->stream));
 	}
-	unsigned long long* st = (unsigned long long*)(res + (size_t)A * h->C + (size_t)h->C + (((size_t)A * h->C + h->C) & 1));
+	unsigned long long* st = (unsigned long long*)(res + n_pad);
 	CK (cudaMemcpyAsync (st, d_stats (h), 2 * sizeof (unsigned long long), cudaMemcpyDeviceToHost, h->stream));
 	CK (cudaStreamSynchronize (h->stream));
 	prof_resolve (h);
@@ -585,8 +646,10 @@ angle_schedule (phaserot* h, int ang_start, int ang_end, int ang_stride, std::ve
  */
 int
 sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frames, long long t_end, bool first_block,
-            const float* hist, int ang_start, int ang_end, int ang_stride, int chn, int pcm_bytes = 0 /* host src is int16 (2) / int32 (4) PCM */)
+            const float* hist, int ang_start, int ang_end, int ang_stride, int chn, int fmt = PHASEROT_PCM_F32 /* host src: PHASEROT_PCM_* */)
 {
+	// bytes per sample on the host side (and on the bus); 0 = float32, no conversion pass
+	const int pcm_bytes = fmt == PHASEROT_PCM_S16 ? 2 : fmt == PHASEROT_PCM_S32 ? 4 : fmt == PHASEROT_PCM_S24 ? 3 : 0;
 	if (chn >= h->C) {
 		return PHASEROT_E_INVAL;
 	}
@@ -648,7 +711,8 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 	// 3.7 GB.  Host input keeps 8, so that little work is left when the last chunk
 	// has landed.)
 	const long long segs_first = std::max<long long> (1, ((long long)h->n_sm * 8) / nchan);
-	const long long segs_max   = !src_is_device ? segs_first : (OS_is_digital (h) ? 16 : 2) * segs_first; // true-peak: the list holds OS + 1 points per sample
+	long long       segs_max   = !src_is_device ? segs_first : (OS_is_digital (h) ? 16 : 2) * segs_first; // true-peak: the list holds OS + 1 points per sample
+	if (getenv ("PHASEROT_SEGS_MAX")) segs_max = std::max<long long> (1, atoll (getenv ("PHASEROT_SEGS_MAX")) * h->n_sm / nchan);
 	const long long segs_cap   = std::min (segs_max, std::max<long long> (nseg, 1));
 	const int       OS       = h->OS;
 	h->list_stride           = segs_cap * h->V * 2 * (OS > 1 ? OS + 1 : 1); // true-peak: the sample and OS interpolated points
@@ -862,7 +926,7 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 		p.inter = (const float*)h->d_inter.p;
 		rc      = tp_head ();
 		if (rc) return rc;
-		const long long chunk_frames = std::max<long long> (2, ((8LL << 20) / h->C) & ~1LL); // ~32 MB of floats per chunk
+		const long long chunk_frames = std::max<long long> (4, ((8LL << 20) / h->C) & ~3LL); // ~32 MB of floats per chunk; a multiple of 4 frames keeps every chunk 4-byte aligned at 3 bytes per sample
 		const size_t    bps          = pcm_bytes ? (size_t)pcm_bytes : sizeof (float);      // bytes per sample on the host side
 		cudaPointerAttributes at;
 		const bool pinned = (cudaPointerGetAttributes (&at, src) == cudaSuccess) && (at.type == cudaMemoryTypeHost);
@@ -906,6 +970,8 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 				const unsigned  nb = (unsigned)((ns + 1023) / 1024);
 				if (pcm_bytes == 2) {
 					pcm_to_float_kernel<int16_t><<<nb, 256, 0, h->copy_stream>>> ((const int16_t*)h->d_stage[b].p, d_chunk, ns);
+				} else if (pcm_bytes == 3) {
+					pcm24_to_float_kernel<<<nb, 256, 0, h->copy_stream>>> ((const uint8_t*)h->d_stage[b].p, d_chunk, ns);
 				} else {
 					pcm_to_float_kernel<int32_t><<<nb, 256, 0, h->copy_stream>>> ((const int32_t*)h->d_stage[b].p, d_chunk, ns);
 				}
@@ -1051,6 +1117,19 @@ flush_analyze (phaserot* h)
 	h->an_blocks = 0;
 	h->an_first  = 0;
 	return finish_pending (h);
+}
+
+// pinned staging of one plugin call of n frames: window [C][wstride] | ramp prefix
+// [C][pre_cap] | outputs [C][n] | per-CTA meter maxima [C][n_cta][2]
+constexpr uint32_t kSmallCallMax = 16384;
+inline size_t
+plugin_io_bytes (const phaserot* h, uint32_t n)
+{
+	const size_t keep    = (size_t)h->firlen + h->P;
+	const size_t wstride = (keep + n + 3) & ~(size_t)3;
+	const size_t pre_cap = (size_t)h->P * 20;
+	const size_t n_cta   = ((size_t)n + kStreamOut - 1) / kStreamOut;
+	return sizeof (float) * wstride * h->C + sizeof (float2) * pre_cap * h->C + (n <= kSmallCallMax ? sizeof (float) * ((size_t)n + 2 * n_cta) * h->C : 0) + 64;
 }
 
 // src/phaserotate.c:122-133
@@ -1238,6 +1317,7 @@ phaserot_create (phaserot_t** out, const phaserot_cfg_t* cfg)
 	h->cfg    = *cfg;
 	h->dev    = dev;
 	h->n_sm   = prop.multiProcessorCount;
+	if (const char* e = getenv ("PHASEROT_PAIR_SYNC")) h->pair_sync = atoi (e);
 	h->C      = cfg->n_channels;
 	h->L      = L;
 	h->Lh     = L / 2;
@@ -1270,7 +1350,9 @@ phaserot_create (phaserot_t** out, const phaserot_cfg_t* cfg)
 			break;
 		}
 		h->stream = h->own_stream;
-		rc        = h->d_small.ensure (kSmallBytes);
+		rc        = set_device_attrs (dev);
+		if (rc) break;
+		rc = h->d_small.ensure (kSmallBytes);
 		if (rc) break;
 		if (cudaMemset (h->d_small.p, 0, kSmallBytes) != cudaSuccess) {
 			rc = PHASEROT_E_CUDA;
@@ -1286,6 +1368,14 @@ phaserot_create (phaserot_t** out, const phaserot_cfg_t* cfg)
 				ch.last_const = make_float2 (ch.ca, ch.sa);
 			}
 			h->ptail.assign ((size_t)h->C * (firlen + P), 0.f);
+			// everything a small call (n <= kSmallCallMax frames; LV2 hosts stay below
+			// MAXPERIOD 8192, robtk/jackwrap.c:36) touches is allocated here, so that
+			// run() neither allocates nor locks in steady state, whatever period the
+			// host picks or changes to
+			rc = h->h_io.ensure (plugin_io_bytes (h, kSmallCallMax));
+			if (rc) break;
+			rc = h->d_ring.ensure (sizeof (float) * (size_t)kRing * h->C);
+			if (rc) break;
 		} else {
 			h->ap_hist.assign ((size_t)h->C * L, 0.f);
 		}
@@ -1312,7 +1402,7 @@ phaserot_destroy (phaserot_t* h)
 	                   &h->d_cs, &h->d_peaks, &h->d_ramp, &h->d_chancs, &h->d_tpH, &h->d_ring }) {
 		b->release ();
 	}
-	for (PinBuf* b : { &h->h_stage[0], &h->h_stage[1], &h->h_res, &h->h_io }) {
+	for (PinBuf* b : { &h->h_stage[0], &h->h_stage[1], &h->h_res, &h->h_io, &h->h_cs }) {
 		b->release ();
 	}
 	for (int b = 0; b < 2; ++b) {
@@ -1387,7 +1477,7 @@ phaserot_sweep (phaserot_t* h, const float* interleaved, uint64_t n_frames, int 
 int
 phaserot_sweep_pcm (phaserot_t* h, const void* pcm, int format, uint64_t n_frames, int ang_start, int ang_end, int ang_stride, int chn)
 {
-	if (!h || (!pcm && n_frames) || (format != PHASEROT_PCM_S16 && format != PHASEROT_PCM_S32)) {
+	if (!h || (!pcm && n_frames) || (format != PHASEROT_PCM_S16 && format != PHASEROT_PCM_S32 && format != PHASEROT_PCM_S24)) {
 		return PHASEROT_E_INVAL;
 	}
 	if (h->plugin) {
@@ -1396,7 +1486,7 @@ phaserot_sweep_pcm (phaserot_t* h, const void* pcm, int format, uint64_t n_frame
 	DevGuard        guard (h->dev);
 	const long long F = (long long)n_frames;
 	const long long B = (F + h->L - 1) / h->L;
-	int rc = sweep_core (h, (const float*)pcm, false, F, (B + 1) * h->L, B > 0, nullptr, ang_start, ang_end, ang_stride, chn, format == PHASEROT_PCM_S16 ? 2 : 4);
+	int rc = sweep_core (h, (const float*)pcm, false, F, (B + 1) * h->L, B > 0, nullptr, ang_start, ang_end, ang_stride, chn, format);
 	if (rc) return rc;
 	return finish_pending (h);
 }
@@ -1514,6 +1604,41 @@ phaserot_sweep_shard_device (phaserot_t* h, const float* d_interleaved, uint64_t
 	const long long B     = (F + h->L - 1) / h->L;
 	const long long t_end = last ? (B + 1) * h->L : F;
 	return sweep_core (h, d_interleaved, true, F, t_end, first != 0 && B > 0, hist, ang_start, ang_end, ang_stride, chn);
+}
+
+int
+phaserot_sweep_shard (phaserot_t* h, const void* data, int format, uint64_t n_frames, const float* hist, int first, int last,
+                      int ang_start, int ang_end, int ang_stride, int chn)
+{
+	if (!h || (!data && n_frames) || format < PHASEROT_PCM_F32 || format > PHASEROT_PCM_S24) {
+		return PHASEROT_E_INVAL;
+	}
+	if (h->plugin) {
+		return PHASEROT_E_STATE;
+	}
+	const long long F = (long long)n_frames;
+	if (!last && (F % h->L) != 0) {
+		return PHASEROT_E_INVAL;
+	}
+	DevGuard        guard (h->dev);
+	const long long B     = (F + h->L - 1) / h->L;
+	const long long t_end = last ? (B + 1) * h->L : F;
+	return sweep_core (h, (const float*)data, false, F, t_end, first != 0 && B > 0, hist, ang_start, ang_end, ang_stride, chn, format);
+}
+
+int
+phaserot_plugin_angle (phaserot_t* h, float* angle_turns)
+{
+	if (!h || !angle_turns) {
+		return PHASEROT_E_INVAL;
+	}
+	if (!h->plugin) {
+		return PHASEROT_E_STATE;
+	}
+	for (int c = 0; c < h->C; ++c) {
+		angle_turns[c] = h->pch[(size_t)c].angle;
+	}
+	return PHASEROT_OK;
 }
 
 int
@@ -1726,10 +1851,9 @@ phaserot_process_levels (phaserot_t* h, const float* const* in, float* const* ou
 	const uint32_t first_np = (uint32_t)(t0 / P);                  // partition being filled at t0
 	const uint32_t n_comp   = (uint32_t)((t0 + n) / P) - first_np; // partitions completing in this call
 	const size_t   pre_cap  = (size_t)P * 20;                      // a full 180 degree ramp is <= 9 partitions (src:295)
-	const bool     small    = n <= 16384;
+	const bool     small    = n <= kSmallCallMax;
 	const size_t   n_cta    = (n + kStreamOut - 1) / kStreamOut; // CTAs per channel of the small-call kernel
-	const size_t   io_bytes = sizeof (float) * wstride * C + sizeof (float2) * pre_cap * C + (small ? sizeof (float) * ((size_t)n + 2 * n_cta) * C : 0) + 64;
-	int            rc       = h->h_io.ensure (io_bytes);
+	int            rc       = h->h_io.ensure (plugin_io_bytes (h, n)); // no-op for small calls: sized in create()
 	if (rc) return rc;
 	float*  W    = (float*)h->h_io.p;
 	float2* pre  = (float2*)(W + wstride * C);
@@ -1792,11 +1916,6 @@ phaserot_process_levels (phaserot_t* h, const float* const* in, float* const* ou
 		// outputs back to it.
 		const int    nodd = h->Lh;
 		const size_t smem = sizeof (float) * (3 * (size_t)nodd + kStreamOut + 128);
-		static bool  attr = false;
-		if (!attr) {
-			CK (cudaFuncSetAttribute (fir_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-			attr = true;
-		}
 		rc = h->d_ring.ensure (sizeof (float) * (size_t)kRing * C);
 		if (rc) return rc;
 		if (!h->ring_valid) {
@@ -1940,11 +2059,274 @@ phaserot_process_levels (phaserot_t* h, const float* const* in, float* const* ou
 	return PHASEROT_OK;
 }
 
+// ---------------------------------------------------------------------------
+// device group: one stream, several GPUs of one process (sample-range shards)
+// ---------------------------------------------------------------------------
+} // extern "C"
+
+struct phaserot_group {
+	std::vector<phaserot*>   h;
+	std::vector<cudaEvent_t> ev;   // "sweep of device i enqueued work is complete", recorded on h[i]->stream
+	std::vector<char>        peer; // device 0 can read device i's memory directly
+	DevBuf                   d_gather; // device 0: copies of the other tables when peer access is missing
+};
+
+namespace {
+
+// float32 history in front of a shard from a host stream in any PHASEROT_PCM_* format
+void
+shard_history (const void* data, int fmt, long long f0, int L, int C, std::vector<float>& out)
+{
+	out.resize ((size_t)L * C);
+	const size_t n = (size_t)L * C, i0 = (size_t)(f0 - L) * C;
+	switch (fmt) {
+		case PHASEROT_PCM_S16: {
+			const int16_t* q = (const int16_t*)data + i0;
+			for (size_t i = 0; i < n; ++i) out[i] = (float)q[i] * (1.f / 32768.f);
+		} break;
+		case PHASEROT_PCM_S32: {
+			const int32_t* q = (const int32_t*)data + i0;
+			for (size_t i = 0; i < n; ++i) out[i] = (float)q[i] * (1.f / 2147483648.f);
+		} break;
+		case PHASEROT_PCM_S24: {
+			const uint8_t* q = (const uint8_t*)data + 3 * i0;
+			for (size_t i = 0; i < n; ++i) {
+				const int32_t v = (int32_t)(((uint32_t)q[3 * i] << 8) | ((uint32_t)q[3 * i + 1] << 16) | ((uint32_t)q[3 * i + 2] << 24));
+				out[i]          = (float)v * (1.f / 2147483648.f);
+			}
+		} break;
+		default: memcpy (out.data (), (const float*)data + i0, sizeof (float) * n); break;
+	}
+}
+
+} // namespace
+
+extern "C" {
+
+int
+phaserot_group_create (phaserot_group_t** out, const phaserot_cfg_t* cfg, const int* devices, int n_devices)
+{
+	if (!out) {
+		return PHASEROT_E_INVAL;
+	}
+	*out = nullptr;
+	if (!cfg || n_devices < 1 || n_devices > 16 || cfg->mode != PHASEROT_MODE_CLI) {
+		return PHASEROT_E_INVAL;
+	}
+	phaserot_group* g = new (std::nothrow) phaserot_group ();
+	if (!g) {
+		return PHASEROT_E_NOMEM;
+	}
+	// PHASEROT_GROUP_DEVICES="0,0,1": device list override when the caller passes none
+	// (lets a one-GPU box exercise `phase-rotate --gpus 2`: two handles on one device)
+	std::vector<int> env_dev;
+	if (!devices) {
+		if (const char* e = getenv ("PHASEROT_GROUP_DEVICES")) {
+			for (const char* q = e; *q;) {
+				env_dev.push_back (atoi (q));
+				while (*q && *q != ',') ++q;
+				if (*q == ',') ++q;
+			}
+			if ((int)env_dev.size () >= n_devices) {
+				devices = env_dev.data ();
+			}
+		}
+	}
+	int rc = PHASEROT_OK;
+	for (int i = 0; i < n_devices && rc == PHASEROT_OK; ++i) {
+		phaserot_cfg_t c = *cfg;
+		c.device         = devices ? devices[i] : i;
+		phaserot*      h = nullptr;
+		rc               = phaserot_create (&h, &c);
+		if (rc == PHASEROT_OK) {
+			g->h.push_back (h);
+			DevGuard    guard (h->dev);
+			cudaEvent_t e = nullptr;
+			if (cudaEventCreateWithFlags (&e, cudaEventDisableTiming) != cudaSuccess) {
+				rc = PHASEROT_E_CUDA;
+			}
+			g->ev.push_back (e);
+		}
+	}
+	if (rc == PHASEROT_OK) {
+		// peer access from the first device to the others (NVLink / NVSwitch on a B200 box)
+		g->peer.assign (g->h.size (), 0);
+		DevGuard guard (g->h[0]->dev);
+		for (size_t i = 1; i < g->h.size (); ++i) {
+			int can = 0;
+			if (g->h[i]->dev == g->h[0]->dev) {
+				g->peer[i] = 1;
+			} else if (cudaDeviceCanAccessPeer (&can, g->h[0]->dev, g->h[i]->dev) == cudaSuccess && can) {
+				const cudaError_t e = cudaDeviceEnablePeerAccess (g->h[i]->dev, 0);
+				if (e == cudaSuccess || e == cudaErrorPeerAccessAlreadyEnabled) {
+					g->peer[i] = 1;
+				}
+				cudaGetLastError ();
+			}
+		}
+	}
+	if (rc != PHASEROT_OK) {
+		phaserot_group_destroy (g);
+		return rc;
+	}
+	*out = g;
+	return PHASEROT_OK;
+}
+
+void
+phaserot_group_destroy (phaserot_group_t* g)
+{
+	if (!g) {
+		return;
+	}
+	for (size_t i = 0; i < g->h.size (); ++i) {
+		if (i < g->ev.size () && g->ev[i]) {
+			DevGuard guard (g->h[i]->dev);
+			cudaEventDestroy (g->ev[i]);
+		}
+	}
+	if (!g->h.empty ()) {
+		DevGuard guard (g->h[0]->dev);
+		g->d_gather.release ();
+	}
+	for (phaserot* h : g->h) {
+		phaserot_destroy (h);
+	}
+	delete g;
+}
+
+int
+phaserot_group_size (const phaserot_group_t* g)
+{
+	return g ? (int)g->h.size () : 0;
+}
+
+phaserot_t*
+phaserot_group_handle (phaserot_group_t* g, int i)
+{
+	return (g && i >= 0 && (size_t)i < g->h.size ()) ? g->h[(size_t)i] : nullptr;
+}
+
+int
+phaserot_group_reset (phaserot_group_t* g)
+{
+	if (!g) {
+		return PHASEROT_E_INVAL;
+	}
+	for (phaserot* h : g->h) {
+		const int rc = phaserot_reset (h);
+		if (rc) return rc;
+	}
+	return PHASEROT_OK;
+}
+
+int
+phaserot_group_sweep (phaserot_group_t* g, const void* data, int format, uint64_t n_frames, int ang_start, int ang_end, int ang_stride, int chn)
+{
+	if (!g || (!data && n_frames) || format < PHASEROT_PCM_F32 || format > PHASEROT_PCM_S24) {
+		return PHASEROT_E_INVAL;
+	}
+	phaserot*       h0    = g->h[0];
+	const int       n     = (int)g->h.size ();
+	const long long F     = (long long)n_frames;
+	const long long align = (long long)phaserot_shard_align (h0);
+	// equal shards cut on the FFT segment grid; short files use fewer devices
+	long long per = (F + n - 1) / n;
+	per           = std::max (align, (per + align - 1) / align * align);
+	const int used = (int)std::max<long long> (1, std::min<long long> (n, (F + per - 1) / per));
+	const size_t bps = format == PHASEROT_PCM_S16 ? 2 : format == PHASEROT_PCM_S24 ? 3 : 4;
+
+	std::vector<int>         rcs ((size_t)used, PHASEROT_OK);
+	std::vector<std::string> errs ((size_t)used);
+	auto shard = [&] (int i) {
+		phaserot*       h   = g->h[(size_t)i];
+		const long long f0  = (long long)i * per;
+		const long long nf  = std::max<long long> (0, std::min (per, F - f0));
+		const bool      lst = i == used - 1;
+		std::vector<float> hist;
+		if (i > 0) {
+			shard_history (data, format, f0, h->L, h->C, hist);
+		}
+		DevGuard        guard (h->dev);
+		const long long B     = (nf + h->L - 1) / h->L;
+		const long long t_end = lst ? (B + 1) * h->L : nf;
+		int rc = sweep_core (h, (const float*)((const char*)data + bps * (size_t)f0 * h->C), false, nf, t_end, i == 0 && B > 0,
+		                     i > 0 ? hist.data () : nullptr, ang_start, ang_end, ang_stride, chn, format);
+		if (rc == PHASEROT_OK && cudaEventRecord (g->ev[(size_t)i], h->stream) != cudaSuccess) {
+			rc = PHASEROT_E_CUDA;
+		}
+		rcs[(size_t)i]  = rc;
+		errs[(size_t)i] = g_last_error; // thread-local in the worker
+	};
+	// one host thread per device: the chunked uploads of all shards are in flight together
+	std::vector<std::thread> th;
+	for (int i = 1; i < used; ++i) th.emplace_back (shard, i);
+	shard (0);
+	for (auto& t : th) t.join ();
+	for (int i = 0; i < used; ++i) {
+		if (rcs[(size_t)i]) {
+			snprintf (g_last_error, sizeof (g_last_error), "device %d: %s", g->h[(size_t)i]->dev, errs[(size_t)i].c_str ());
+			return rcs[(size_t)i];
+		}
+	}
+	// handles that got no shard keep an empty table
+	if (used > 1) {
+		DevGuard     guard (h0->dev);
+		const size_t cnt = (size_t)std::max (h0->pend_A, 1) * h0->C + (size_t)h0->C;
+		PeerTabs     pt;
+		pt.n = 0;
+		size_t n_copy = 0;
+		for (int i = 1; i < used; ++i) n_copy += g->peer[(size_t)i] ? 0 : 1;
+		if (n_copy) {
+			const int rc = g->d_gather.ensure (sizeof (unsigned) * cnt * n_copy);
+			if (rc) return rc;
+		}
+		size_t slot = 0;
+		for (int i = 1; i < used; ++i) {
+			phaserot* h = g->h[(size_t)i];
+			CK (cudaStreamWaitEvent (h0->stream, g->ev[(size_t)i], 0));
+			if (g->peer[(size_t)i]) {
+				pt.p[pt.n++] = (const unsigned*)h->d_peaks.p;
+			} else {
+				unsigned* dst = (unsigned*)g->d_gather.p + cnt * slot++;
+				CK (cudaMemcpyPeerAsync (dst, h0->dev, h->d_peaks.p, h->dev, sizeof (unsigned) * cnt, h0->stream));
+				pt.p[pt.n++] = dst;
+			}
+		}
+		{
+			ProfScope ps (h0, 5);
+			peer_max_kernel<<<(unsigned)((cnt + 255) / 256), 256, 0, h0->stream>>> ((unsigned*)h0->d_peaks.p, pt, (long long)cnt);
+		}
+		CK (cudaGetLastError ());
+		++h0->stats.kernel_launches;
+	}
+	int rc = finish_pending (h0);
+	if (rc) return rc;
+	for (int i = 1; i < used; ++i) {
+		// the other devices' tables have been consumed on device 0 (finish_pending waited for it)
+		phaserot* h = g->h[(size_t)i];
+		DevGuard  guard (h->dev);
+		CK (cudaStreamSynchronize (h->stream));
+		prof_resolve (h);
+		h->pending = false;
+	}
+	return PHASEROT_OK;
+}
+
+int
+phaserot_group_peaks (phaserot_group_t* g, float* out)
+{
+	if (!g || !out) {
+		return PHASEROT_E_INVAL;
+	}
+	return phaserot_peaks (g->h[0], out);
+}
+
 void*
 phaserot_alloc_host (uint64_t bytes)
 {
 	void* p = nullptr;
-	if (cudaHostAlloc (&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+	if (cudaHostAlloc (&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { // page-locked for every device (device groups)
 		cudaGetLastError ();
 		return nullptr;
 	}

@@ -39,18 +39,26 @@
 
 namespace {
 
-constexpr int kSubsample = 2;               // cli:38
-constexpr int kMaxSample = 180 * kSubsample; // cli:39
+// Angle grid: SUBSAMPLE 2 / MAXSAMPLE 360 in the reference (cli:38-39), i.e. half
+// degrees.  `--subsample N` (long option of this backend only) selects 1/N degree
+// steps; every place the reference uses the two constants reads these instead.
+int kSubsample = 2;
+int kMaxSample = 180 * 2;
 
 struct Options {
 	const char*  angles_arg = nullptr;
-	int          stride     = 12 * kSubsample; // cli:597
+	int          stride     = 0;
+	bool         stride_set = false; // default: 12 degrees (cli:597)
 	int          verbose    = 0;
 	bool         link       = false;
 	unsigned int blksiz     = 0;
 	const char*  in_path    = nullptr;
 	const char*  out_path   = nullptr;
-	int          oversample = 0; // --true-peak[=2|4]: opt-in long option of this backend, not in the reference
+	// opt-in long options of this backend; the reference's own options are unchanged
+	int          oversample  = 0;     // --true-peak[=2|4]
+	int          subsample   = 2;     // --subsample N: 1/N degree grid (BASELINE configs 3 and 5 use 10 and 100)
+	int          gpus        = 1;     // --gpus N: sample-range shards over N devices (0 = all)
+	bool         fixed_write = false; // --fixed-write: write loop without the reference's two quirks (cli:985, cli:973)
 };
 
 float
@@ -131,6 +139,9 @@ parse_options (int argc, char** argv)
 		{ "version", no_argument, 0, 'V' },
 		{ "verbose", no_argument, 0, 'v' },
 		{ "true-peak", optional_argument, 0, 1000 }, // new, long-only: the reference's options are unchanged
+		{ "subsample", required_argument, 0, 1001 },
+		{ "gpus", required_argument, 0, 1002 },
+		{ "fixed-write", no_argument, 0, 1003 },
 		{ 0, 0, 0, 0 },
 	};
 	int c;
@@ -140,7 +151,10 @@ parse_options (int argc, char** argv)
 			case 'f': o.blksiz = (unsigned int)atoi (optarg); break;
 			case 'h': print_help (); break;
 			case 'l': o.link = true; break;
-			case 's': o.stride = atoi (optarg); break;
+			case 's':
+				o.stride     = atoi (optarg);
+				o.stride_set = true;
+				break;
 			case 'V':
 				printf ("phase-rotate version %s\n\n", VERSION);
 				printf ("Copyright (C) GPL 2021 Robin Gareus <robin@gareus.org>\n");
@@ -152,8 +166,26 @@ parse_options (int argc, char** argv)
 					die ("Error: --true-peak takes an oversampling factor of 2 or 4.\n");
 				}
 				break;
+			case 1001:
+				o.subsample = atoi (optarg);
+				if (o.subsample < 1 || o.subsample > 1000) {
+					die ("Error: --subsample takes a grid density of 1 .. 1000 steps per degree.\n");
+				}
+				break;
+			case 1002:
+				o.gpus = atoi (optarg);
+				if (o.gpus < 0 || o.gpus > 16) {
+					die ("Error: --gpus takes a device count of 0 (all) .. 16.\n");
+				}
+				break;
+			case 1003: o.fixed_write = true; break;
 			default: die ("Error: unrecognized option. See --help for usage information.\n");
 		}
+	}
+	kSubsample = o.subsample;
+	kMaxSample = 180 * kSubsample;
+	if (!o.stride_set) {
+		o.stride = 12 * kSubsample;
 	}
 	if (optind + 1 > argc) {
 		die ("Error: Missing parameter. See --help for usage information.\n");
@@ -340,10 +372,15 @@ main (int argc, char** argv)
 	// does (cli:573).
 	const uint64_t frames  = nfo.frames > 0 ? (uint64_t)nfo.frames : 0;
 	const int      subfmt  = nfo.format & SF_FORMAT_SUBMASK;
+	// 24-bit samples of a little-endian container (WAV, RF64, W64; format word without an
+	// endianness override) travel packed, 3 bytes each, exactly as sf_read_raw delivers them
+	const int      major   = nfo.format & SF_FORMAT_TYPEMASK;
+	const bool     raw24   = subfmt == SF_FORMAT_PCM_24 && (nfo.format & 0x30000000) == 0 && (major == SF_FORMAT_WAV || major == 0x220000 /* RF64 */ || major == 0x0B0000 /* W64 */);
 	const int      pcm_fmt = (find_min && !opt.out_path && subfmt == SF_FORMAT_PCM_16)                                 ? PHASEROT_PCM_S16
+	                         : (find_min && !opt.out_path && raw24)                                                     ? PHASEROT_PCM_S24
 	                         : (find_min && !opt.out_path && (subfmt == SF_FORMAT_PCM_24 || subfmt == SF_FORMAT_PCM_32)) ? PHASEROT_PCM_S32
 	                                                                                                                      : 0;
-	const size_t   ssize   = pcm_fmt == PHASEROT_PCM_S16 ? sizeof (short) : sizeof (float); // int and float are both 4 bytes
+	const size_t   ssize   = pcm_fmt == PHASEROT_PCM_S16 ? sizeof (short) : pcm_fmt == PHASEROT_PCM_S24 ? 3 : sizeof (float); // int and float are both 4 bytes
 	const size_t   fbytes  = std::max<size_t> (ssize * (size_t)frames * (size_t)C, 16);
 	float*         audio   = (float*)phaserot_alloc_host (fbytes);
 	bool           pinned  = audio != nullptr;
@@ -359,6 +396,8 @@ main (int argc, char** argv)
 		sf_count_t       n;
 		if (pcm_fmt == PHASEROT_PCM_S16) {
 			n = sf_readf_short (infile, (short*)audio + got * (uint64_t)C, want);
+		} else if (pcm_fmt == PHASEROT_PCM_S24) {
+			n = sf_read_raw (infile, (char*)audio + 3 * got * (uint64_t)C, want * 3 * (sf_count_t)C) / (3 * (sf_count_t)C);
 		} else if (pcm_fmt == PHASEROT_PCM_S32) {
 			n = sf_readf_int (infile, (int*)audio + got * (uint64_t)C, want);
 		} else {
@@ -380,8 +419,31 @@ main (int argc, char** argv)
 	cfg.subsample   = kSubsample;
 	cfg.device      = -1;
 	cfg.oversample  = opt.oversample;
-	phaserot_t* pr  = nullptr;
-	check (phaserot_create (&pr, &cfg), "cannot initialise the CUDA backend");
+	phaserot_t*       pr  = nullptr;
+	phaserot_group_t* grp = nullptr;
+	if (opt.gpus != 1) {
+		// --gpus N: one contiguous shard of the file per device, tables combined on the
+		// first device over NVLink (phaserot_group_sweep); rendering stays on the first device
+		int ndev = opt.gpus;
+		if (ndev == 0) {
+			phaserot_group_t* probe = nullptr;
+			for (ndev = 16; ndev > 1; --ndev) { // the largest group the box can form
+				if (phaserot_group_create (&probe, &cfg, nullptr, ndev) == PHASEROT_OK) {
+					break;
+				}
+			}
+			grp = probe;
+		}
+		if (!grp) {
+			check (phaserot_group_create (&grp, &cfg, nullptr, ndev), "cannot initialise the CUDA backend");
+		}
+		pr = phaserot_group_handle (grp, 0);
+		if (opt.verbose > 1) {
+			fprintf (vfd, "Analyzing on %d GPUs\n", phaserot_group_size (grp));
+		}
+	} else {
+		check (phaserot_create (&pr, &cfg), "cannot initialise the CUDA backend");
+	}
 
 	if (find_min) {
 		const int stride = opt.stride;
@@ -389,7 +451,9 @@ main (int argc, char** argv)
 			fprintf (vfd, "Analyzing using %d process threads, stride = %d\n", C, stride);
 		}
 		// one pass, every grid index (index 0 = raw peak, cli:413-414)
-		if (pcm_fmt) {
+		if (grp) {
+			check (phaserot_group_sweep (grp, audio, pcm_fmt, F, 0, kMaxSample, 1, -1), "analysis failed");
+		} else if (pcm_fmt) {
 			check (phaserot_sweep_pcm (pr, audio, pcm_fmt, F, 0, kMaxSample, 1, -1), "analysis failed");
 		} else {
 			check (phaserot_sweep (pr, audio, F, 0, kMaxSample, 1, -1), "analysis failed");
@@ -556,7 +620,34 @@ main (int argc, char** argv)
 		};
 
 		std::vector<float> last_out (bs, 0.f); // processed block the reference would still hold in `buf`
-		if (n_full > 0) {
+		if (opt.fixed_write) {
+			// --fixed-write: the latency-compensated render y[t + L/2], t in [0, F), as the
+			// write loop intends it: the trim counts FRAMES (the reference offsets the
+			// interleaved buffer by `latency` floats, cli:985: channels > 1 start at frame
+			// latency / channels) and a short last block is always zero padded (cli:973
+			// leaves the previous block's output behind it when it is longer than the latency)
+			const uint64_t nb = (F + L - 1) / L + 1;
+			float*         y  = (float*)phaserot_alloc_host (sizeof (float) * bs * nb);
+			const bool     yp = y != nullptr;
+			if (!y) {
+				y = (float*)malloc (sizeof (float) * bs * nb);
+			}
+			if (!y) {
+				die ("Out of memory\n");
+			}
+			check (phaserot_render (pr, audio, F, angles.data (), 1, y), "render failed");
+			if ((sf_count_t)F != sf_writef_float (outfile, y + (size_t)latency * (size_t)C, (sf_count_t)F)) {
+				fprintf (stderr, "Error writing to output file.\n");
+			}
+			if (yp) {
+				phaserot_free_host (y);
+			} else {
+				free (y);
+			}
+			sf_close (outfile);
+			outfile = nullptr;
+		}
+		if (outfile && n_full > 0) {
 			float* y = (float*)phaserot_alloc_host (sizeof (float) * bs * n_full);
 			bool   y_pinned = y != nullptr;
 			if (!y) {
@@ -576,7 +667,7 @@ main (int argc, char** argv)
 				free (y);
 			}
 		}
-		if (rem > 0 && !failed) {
+		if (outfile && rem > 0 && !failed) {
 			// short last block (cli:968-990): frames beyond `rem` keep the previous
 			// processed block unless rem < latency, in which case they are zeroed
 			std::vector<float>& buf = last_out;
@@ -590,7 +681,7 @@ main (int argc, char** argv)
 			check (phaserot_apply (pr, buf.data (), angles.data ()), "render failed");
 			write_block (buf.data (), n);
 		}
-		const sf_count_t nflush = (sf_count_t)latency - pad; // cli:993-1001
+		const sf_count_t nflush = outfile ? (sf_count_t)latency - pad : 0; // cli:993-1001
 		if (nflush > 0) {
 			std::vector<float> z (bs, 0.f);
 			check (phaserot_apply (pr, z.data (), angles.data ()), "render failed");
@@ -598,10 +689,16 @@ main (int argc, char** argv)
 				fprintf (stderr, "Error writing to output file.\n");
 			}
 		}
-		sf_close (outfile);
+		if (outfile) {
+			sf_close (outfile);
+		}
 	}
 
-	phaserot_destroy (pr);
+	if (grp) {
+		phaserot_group_destroy (grp);
+	} else {
+		phaserot_destroy (pr);
+	}
 	sf_close (infile);
 	if (pinned) {
 		phaserot_free_host (audio);

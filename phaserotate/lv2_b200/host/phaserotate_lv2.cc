@@ -354,6 +354,12 @@ run (LV2_Handle instance, uint32_t n_samples)
 	// --- audio: all channels in one backend call --------------------------
 	float        lvl_in[kMaxChannels] = { 0, 0 };
 	float        angles[kMaxChannels] = { 0, 0 };
+	// the backend's ramp state as process_channel() finds it at the start of this call (Channel::angle)
+	float        angle_state[kMaxChannels] = { 0, 0 };
+	if (phaserot_plugin_angle (p->dsp, angle_state) != PHASEROT_OK) {
+		angle_state[0] = p->target_state[0];
+		angle_state[1] = p->target_state[1];
+	}
 	const float* ins[kMaxChannels]    = { nullptr, nullptr };
 	float*       outs[kMaxChannels]   = { nullptr, nullptr };
 	for (uint32_t c = 0; c < p->n_chn; ++c) {
@@ -369,7 +375,7 @@ run (LV2_Handle instance, uint32_t n_samples)
 			ch.m_out.momentary        = 0;
 			ch.reset_delay -= (int)n_samples;
 		}
-		if (target != p->target_state[c]) {
+		if (target != angle_state[c]) { // src:611: re-armed on every call while the ramp has not arrived
 			ch.reset_delay = (int)(p->latency + n_samples);
 		}
 		ch.last_target = target;
@@ -384,9 +390,7 @@ run (LV2_Handle instance, uint32_t n_samples)
 		}
 	}
 	for (uint32_t c = 0; c < p->n_chn; ++c) {
-		// the backend ramps towards the target like the reference; once a whole
-		// partition has been processed at the target the state equals it.  For the
-		// meter-reset heuristic it is enough to remember the last requested target.
+		// fallback mirror of the angle state, used only if phaserot_plugin_angle() fails
 		p->target_state[c] = p->ch[c].last_target;
 	}
 

@@ -102,6 +102,7 @@ int         sf_close (SNDFILE* sndfile);
 sf_count_t  sf_readf_float (SNDFILE* sndfile, float* ptr, sf_count_t frames);
 sf_count_t  sf_readf_short (SNDFILE* sndfile, short* ptr, sf_count_t frames); /* 16-bit PCM files: the samples as stored */
 sf_count_t  sf_readf_int (SNDFILE* sndfile, int* ptr, sf_count_t frames);     /* integer PCM files: samples left-justified in 32 bits */
+sf_count_t  sf_read_raw (SNDFILE* sndfile, void* ptr, sf_count_t bytes);          /* the data chunk as stored */
 sf_count_t  sf_writef_float (SNDFILE* sndfile, const float* ptr, sf_count_t frames);
 sf_count_t  sf_seek (SNDFILE* sndfile, sf_count_t frames, int whence);
 const char* sf_strerror (SNDFILE* sndfile);

@@ -339,6 +339,26 @@ read_pcm (SNDFILE* s, void* ptr, sf_count_t frames, int out_bytes)
 	return frames;
 }
 
+/* libsndfile: sf_read_raw copies `bytes` bytes of the data chunk as stored (a whole number of frames). */
+sf_count_t
+sf_read_raw (SNDFILE* s, void* ptr, sf_count_t bytes)
+{
+	if (!s || s->mode != SFM_READ || bytes <= 0 || s->mem) {
+		return 0;
+	}
+	const sf_count_t fb = (sf_count_t)s->bytes_per_sample * s->info.channels;
+	sf_count_t       frames = bytes / fb;
+	if (s->pos + frames > s->info.frames) {
+		frames = s->info.frames - s->pos;
+	}
+	if (frames <= 0) {
+		return 0;
+	}
+	const size_t got = fread (ptr, (size_t)fb, (size_t)frames, s->fp);
+	s->pos += (sf_count_t)got;
+	return (sf_count_t)got * fb;
+}
+
 sf_count_t
 sf_readf_short (SNDFILE* s, short* ptr, sf_count_t frames)
 {
