@@ -51,30 +51,43 @@ N_PARTIALS = 16
 # synthetic programme material: 16 random-phase partials (1/f), slow AM, noise
 # ---------------------------------------------------------------------------
 
-def _partials(seed):
+def _partials(seed, channels=CHANNELS, n_partials=N_PARTIALS):
     rng = np.random.default_rng(seed)
-    f = np.exp(rng.uniform(np.log(50.0), np.log(15000.0), (CHANNELS, N_PARTIALS)))
-    ph = rng.uniform(0, 1.0, (CHANNELS, N_PARTIALS))
+    f = np.exp(rng.uniform(np.log(50.0), np.log(15000.0), (channels, n_partials)))
+    ph = rng.uniform(0, 1.0, (channels, n_partials))
     amp = 50.0 / f
     amp /= amp.sum(axis=1, keepdims=True)
     return f, ph, amp
 
 
-def gen_chunk_torch(torch, chunk_id, device, seed=43):
-    """Frames [chunk_id*GEN_CHUNK, (chunk_id+1)*GEN_CHUNK) -> [GEN_CHUNK, CHANNELS] float32 on `device`."""
-    f, ph, amp = _partials(seed)
-    t = torch.arange(chunk_id * GEN_CHUNK, (chunk_id + 1) * GEN_CHUNK, device=device, dtype=torch.float64) / SR
-    out = torch.empty((GEN_CHUNK, CHANNELS), device=device, dtype=torch.float32)
+def gen_chunk_torch(torch, chunk_id, device, seed=43, channels=CHANNELS, sr=SR, n_partials=N_PARTIALS):
+    """Frames [chunk_id*GEN_CHUNK, (chunk_id+1)*GEN_CHUNK) -> [GEN_CHUNK, channels] float32 on `device`."""
+    f, ph, amp = _partials(seed, channels, n_partials)
+    t = torch.arange(chunk_id * GEN_CHUNK, (chunk_id + 1) * GEN_CHUNK, device=device, dtype=torch.float64) / sr
+    out = torch.empty((GEN_CHUNK, channels), device=device, dtype=torch.float32)
     g = torch.Generator(device=device)
     g.manual_seed(seed * 1000003 + chunk_id)
-    for c in range(CHANNELS):
+    for c in range(channels):
         acc = torch.zeros(GEN_CHUNK, device=device, dtype=torch.float32)
-        for k in range(N_PARTIALS):
+        for k in range(n_partials):
             frac = torch.frac(t * float(f[c, k]) + float(ph[c, k])).to(torch.float32)
             acc += float(amp[c, k]) * torch.sin(frac * (2.0 * np.pi))
         env = 0.6 + 0.4 * torch.sin((torch.frac(t * 0.37) * (2.0 * np.pi)).to(torch.float32) + float(c))
         noise = torch.randn(GEN_CHUNK, device=device, dtype=torch.float32, generator=g)
         out[:, c] = 0.8 * acc * env + 0.02 * noise
+    return out
+
+
+def gen_range_torch(torch, f0, f1, device, **kw):
+    """Frames [f0, f1) of the synthetic stream (any alignment), built from whole generator chunks."""
+    k0, k1 = f0 // GEN_CHUNK, (f1 + GEN_CHUNK - 1) // GEN_CHUNK
+    ch = kw.get("channels", CHANNELS)
+    out = torch.empty((f1 - f0, ch), device=device, dtype=torch.float32)
+    for k in range(k0, k1):
+        c = gen_chunk_torch(torch, k, device, **kw)
+        lo, hi = max(f0, k * GEN_CHUNK), min(f1, (k + 1) * GEN_CHUNK)
+        out[lo - f0:hi - f0] = c[lo - k * GEN_CHUNK:hi - k * GEN_CHUNK]
+        del c
     return out
 
 
@@ -276,17 +289,20 @@ def reference_main(args):
     print(json.dumps(line))
 
 
-def workload_config(args, ref=False):
+def workload_config(args, wl=None, frames_per_gpu=None, world=1, strong=False, ref=False):
+    wl = wl or dict(WORKLOADS["headline"], S=args.subsample, seconds=args.seconds or 3600.0)
+    frames_per_gpu = frames_per_gpu if frames_per_gpu is not None else int(wl["seconds"] * wl["sr"])
+    per = "in total, cut into one sample-range shard per GPU" if strong else "per GPU"
     cfg = {
-        "workload": f"CLI min-peak sweep: stereo 48 kHz, {args.seconds:g} s per GPU, synthetic programme (16 partials x AM + noise), "
-                    f"{1.0 / args.subsample:g} deg grid ({180 * args.subsample} angles), digital peak, blksiz {BLKSIZ}",
-        "frames_per_gpu": int(args.seconds * SR), "channels": CHANNELS, "angles": 180 * args.subsample,
-        "l2": "input (1.38 GB per GPU at 1 h) is larger than the 126 MB L2; no explicit flush",
+        "workload": f"{wl['label']}, {wl['seconds']:g} s {per}, {1.0 / wl['S']:g} deg grid ({180 * wl['S']} angles), blksiz {wl['blksiz']}",
+        "frames_per_gpu": int(frames_per_gpu), "channels": wl["C"], "angles": 180 * wl["S"], "sample_rate": wl["sr"],
+        "l2": f"input ({4e-9 * frames_per_gpu * wl['C']:.2f} GB per GPU) is larger than the 126 MB L2; no explicit flush",
         "sharding": "sample-range, one shard per rank, NCCL max all-reduce of the peak table",
     }
     if ref:
         cfg["reference_arm"] = (f"bounded sample: {args.ref_seconds:g} s of the same material on the reference's own grid "
-                                "(0.5 deg, 360 indices: the reference cannot run finer grids); rate in the same unit")
+                                "(0.5 deg, 360 indices: the reference cannot run finer grids); rate in the same unit; "
+                                "the GPU arm's `same_grid` object is measured on exactly this configuration")
     return cfg
 
 
@@ -433,6 +449,185 @@ def bind_to_gpu_numa_node(torch, local):
     return None
 
 
+WORKLOADS = {
+    # name: channels, sample rate, block size (cli:749-755 from the rate), angle grid density, seconds, partials of the generator
+    "headline": dict(C=CHANNELS, sr=SR, blksiz=BLKSIZ, S=SUBSAMPLE, seconds=3600.0, partials=N_PARTIALS,
+                     label="CLI min-peak sweep: stereo 48 kHz, synthetic programme (16 partials x AM + noise), digital peak"),
+    # BASELINE.json config 5: dense sweep 0.01 deg over 8-channel 192 kHz 1 h audio (22 GB of float32)
+    "config5": dict(C=8, sr=192000, blksiz=32768, S=100, seconds=3600.0, partials=6,
+                    label="BASELINE config 5: dense sweep, 8 ch 192 kHz, synthetic programme (6 partials x AM + noise), digital peak"),
+}
+
+
+class SweepBench:
+    """One sharded analysis pass, timed: every rank owns frames [f0, f1) of a synthetic stream (device resident,
+    generated by absolute position), the blksiz frames in front of it as history, and one handle; a step is
+    reset -> phaserot_sweep_shard_device -> NCCL max all-reduce of the device table -> table read-back."""
+
+    def __init__(self, torch, dist, capi, wl, f0, f1, first, last, rank, world, local, flags=0, seed=43):
+        self.torch, self.dist, self.capi, self.wl = torch, dist, capi, wl
+        self.rank, self.world, self.local, self.first, self.last = rank, world, local, first, last
+        self.dev = torch.device("cuda", local)
+        self.kw = dict(seed=seed, channels=wl["C"], sr=wl["sr"], n_partials=wl["partials"])
+        self.frames = f1 - f0
+        L = wl["blksiz"]
+        self.x = gen_range_torch(torch, f0, f1, self.dev, **self.kw) if f1 > f0 else torch.zeros((0, wl["C"]), device=self.dev)
+        self.hist = gen_range_torch(torch, f0 - L, f0, self.dev, **self.kw) if (f0 >= L and not first) else None
+        self.hist_ptr = self.hist.data_ptr() if self.hist is not None else None
+        torch.cuda.synchronize()
+        self.flags = flags
+        self.h = capi.Phaserot(mode=capi.MODE_CLI, n_channels=wl["C"], blksiz=L, subsample=wl["S"], device=local, flags=flags)
+        self.stream = torch.cuda.current_stream()
+        self.h.set_stream(self.stream.cuda_stream)
+        self.tables = {}
+        self.A = 180 * wl["S"]
+
+    def combine(self, handle):
+        """NCCL max all-reduce, in place, on the handle's device-resident table of the pending sweep
+        (per-angle maxima + raw peaks; phaserot_pending_table): no host round trip."""
+        torch = self.torch
+        ptr, nc, na = handle.pending_table()
+        n = nc * na + nc
+        t = self.tables.get((ptr, n))
+        if t is None:
+            class _Dev:
+                __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+            t = self.tables[(ptr, n)] = torch.as_tensor(_Dev(), device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+
+    def step_device(self):
+        h = self.h
+        h.reset()
+        h.sweep_shard_device(self.x.data_ptr(), self.frames, self.hist_ptr, self.first, self.last)
+        if self.world > 1:
+            self.combine(h)
+        return h.peaks()  # sync + D2H of the (combined) table
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, fn, steps, wall=False):
+        torch = self.torch
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        self.barrier()
+        w = time.perf_counter() - w0
+        ms = e0.elapsed_time(e1)
+        # the table read-back is a host sync inside the step; wall and event time agree, keep the larger
+        t = torch.tensor([max(ms / 1e3, w if wall else 0.0)], device=self.dev, dtype=torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def run_device(self, steps, warmup, sampler=None, wall=False):
+        for _ in range(max(warmup, 3)):
+            self.step_device()
+        self.h.reset_stats()
+        if sampler is not None:
+            sampler.start()
+        t = self.timed(self.step_device, steps, wall)
+        clocks = sampler.stop() if sampler is not None else None
+        st = self.h.stats()
+        return t, st, clocks
+
+    def run_e2e(self, steps):
+        """The same pass from pinned HOST memory through the library's chunked, overlapped upload
+        (phaserot_sweep at N = 1, phaserot_sweep_shard per rank at N > 1): H2D of the rank's whole shard and
+        D2H of the table inside the timed region."""
+        torch, capi = self.torch, self.capi
+        xh = torch.empty((self.frames, self.wl["C"]), dtype=torch.float32, pin_memory=True)
+        xh.copy_(self.x)
+        torch.cuda.synchronize()
+        he = capi.Phaserot(mode=capi.MODE_CLI, n_channels=self.wl["C"], blksiz=self.wl["blksiz"], subsample=self.wl["S"], device=self.local, flags=self.flags)
+        if self.world > 1:
+            he.set_stream(self.stream.cuda_stream)  # the sweep and the all-reduce are ordered on one stream
+
+        def step():
+            he.reset()
+            if self.world == 1:
+                he.sweep((xh.data_ptr(), self.frames))
+            else:
+                he.sweep_shard(xh.data_ptr(), self.frames, self.hist_ptr, self.first, self.last)
+                self.combine(he)
+            he.peaks()
+
+        for _ in range(2):
+            step()
+        self.barrier()
+        w0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        self.barrier()
+        t = torch.tensor([time.perf_counter() - w0], device=self.dev, dtype=torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        he.close()
+        del xh
+        return float(t.item())
+
+    def kernel_times(self):
+        self.h.set_profiling(True)
+        self.step_device()
+        kt = self.h.kernel_times()
+        self.h.set_profiling(False)
+        return kt
+
+    def close(self):
+        self.h.close()
+        del self.x
+
+
+def shard_range(capi, wl, total_frames, rank, world, local):
+    """Frames [f0, f1) of rank `rank` when one stream of total_frames is cut on the FFT segment grid."""
+    with capi.Phaserot(mode=capi.MODE_CLI, n_channels=wl["C"], blksiz=wl["blksiz"], subsample=wl["S"], device=local) as h:
+        al = h.shard_align()
+    per = -(-total_frames // world)
+    per = max(al, -(-per // al) * al)
+    f0 = min(total_frames, rank * per)
+    f1 = min(total_frames, (rank + 1) * per)
+    used = max(1, min(world, -(-total_frames // per)))
+    return f0, f1, used
+
+
+def fp2_per_segment():
+    """Packed fp32 warp instructions one segment of the FFT convolution executes (ncu, profiles/ncu_traffic.json)."""
+    try:
+        return float(json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["fftconv_fp2_warp_inst_per_segment"])
+    except Exception:
+        return None
+
+
+def roofline_of(kt, alg_bytes, step_ms, frames, wl, sm_mhz, n_sm=148):
+    conv = kt["fftconv_filter"]
+    peak, peak_src = measured_hbm_peak()
+    achieved = alg_bytes / (conv["ms"] * 1e-3) / 1e9 if conv["ms"] > 0 else 0.0
+    r = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": None,
+         "kernel": "fftconv_kernel<EPI_POINTS>", "peak_source": peak_src,
+         "algorithmic_bytes_per_step_per_gpu": alg_bytes, "kernel_ms_per_step": conv["ms"], "launches_per_step": conv["launches"],
+         "kernel_share_of_step": conv["ms"] / step_ms if step_ms else None,
+         "whole_step_frac": alg_bytes / (step_ms * 1e-3) / 1e9 / peak if step_ms else None,
+         "all_kernels_ms": {k: round(v["ms"], 4) for k, v in kt.items() if v["launches"]}}
+    # second roofline (SURVEY 8d "report both"): share of the kernel's cycles in which the FP32 pipe of an SM sub-partition is
+    # busy with the FFT's packed instructions (2 issue cycles each: FADD2 / FMUL2 / FFMA2 are 64 lane-operations on 32 lanes)
+    fp2 = fp2_per_segment()
+    if fp2 and conv["ms"] > 0 and sm_mhz:
+        V = 16384 - (wl["blksiz"] // 2 if wl["blksiz"] <= 16384 else 8192)
+        segs = -(-(frames // 2 + wl["blksiz"] // 2) // V) * wl["C"]       # segments per pass (bootstrap wave not counted)
+        cyc_busy = segs * fp2 * 2.0 / (4.0 * n_sm)                         # per SM sub-partition
+        cyc_elapsed = conv["ms"] * 1e-3 * sm_mhz * 1e6
+        r["fp32_issue_frac"] = cyc_busy / cyc_elapsed
+        r["fp32_issue_note"] = ("packed fp32 warp instructions per segment (ncu) x 2 cycles / (4 sub-partitions x SMs), over the kernel's "
+                                "elapsed cycles at the sampled SM clock: the FFT is bound by this pipe, not by HBM (DESIGN.md section 4)")
+    return r
+
+
 def gpu_main(args):
     import torch
     import torch.distributed as dist
@@ -445,144 +640,89 @@ def gpu_main(args):
         raise RuntimeError("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    numa = bind_to_gpu_numa_node(torch, local) if world > 1 else None
+    numa = bind_to_gpu_numa_node(torch, local)  # before any page-locked buffer exists: host memory local to the GPU's socket
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    frames = int(args.seconds * SR)
-    frames -= frames % (32768 - BLKSIZ)  # whole blocks, cut on the FFT segment grid (phaserot_shard_align)
-    A = 180 * args.subsample
-    n_chunks = (frames + GEN_CHUNK - 1) // GEN_CHUNK
+    wl = dict(WORKLOADS["config5" if args.config == "5" else "headline"])
+    wl["S"] = args.subsample if args.config != "5" else wl["S"]
+    wl["seconds"] = args.seconds if args.seconds else wl["seconds"]
+    strong = args.scaling == "strong" or args.config == "5"
+    seg2 = 2 * (16384 - (wl["blksiz"] // 2 if wl["blksiz"] <= 16384 else 8192))       # frames per FFT segment
+    total = int(wl["seconds"] * wl["sr"])
+    total -= total % seg2                                                              # whole blocks, cut on the FFT segment grid (phaserot_shard_align)
 
-    # ---- synthesise this rank's shard on the device (absolute stream position = rank * frames)
-    chunk0 = rank * ((frames + GEN_CHUNK - 1) // GEN_CHUNK)
-    x = torch.empty((n_chunks * GEN_CHUNK, CHANNELS), device=dev, dtype=torch.float32)
-    for k in range(n_chunks):
-        x[k * GEN_CHUNK:(k + 1) * GEN_CHUNK] = gen_chunk_torch(torch, chunk0 + k, dev)
-    x = x[:frames].contiguous()
-    hist = None
-    if rank > 0:
-        prev = gen_chunk_torch(torch, chunk0 - 1, dev)
-        # the previous rank's shard ends at frame `frames` of its own chunk range
-        prev_tail_end = frames - (n_chunks - 1) * GEN_CHUNK
-        hist = prev[prev_tail_end - BLKSIZ:prev_tail_end].contiguous()  # stays on the device, read in place
-    hist_ptr = hist.data_ptr() if hist is not None else None
-    torch.cuda.synchronize()
+    def make(wl_, total_, strong_, flags=0):
+        if strong_:
+            f0, f1, used = shard_range(capi, wl_, total_, rank, world, local)
+            return SweepBench(torch, dist, capi, wl_, f0, f1, rank == 0, rank >= used - 1, rank, world, local, flags), total_
+        # weak: rank r owns stretch r of a world x longer stream
+        return SweepBench(torch, dist, capi, wl_, rank * total_, (rank + 1) * total_, rank == 0, rank == world - 1, rank, world, local, flags), total_ * world
 
-    h = capi.Phaserot(mode=capi.MODE_CLI, n_channels=CHANNELS, blksiz=BLKSIZ, subsample=args.subsample, device=local,
-                      flags=capi.FLAG_NO_PRUNE if args.no_prune else 0)
-    stream = torch.cuda.current_stream()
-    h.set_stream(stream.cuda_stream)
-    tables = {}
-
-    def combine_shards(handle):
-        """NCCL max all-reduce, in place, on the handle's device-resident table of the pending
-        sweep (per-angle maxima + raw peaks; phaserot_pending_table): no host round trip."""
-        ptr, nc, na = handle.pending_table()
-        n = nc * na + nc
-        t = tables.get((ptr, n))
-        if t is None:
-            class _Dev:
-                __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
-            t = tables[(ptr, n)] = torch.as_tensor(_Dev(), device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-
-    def step_device():
-        h.reset()
-        h.sweep_shard_device(x.data_ptr(), frames, hist_ptr, rank == 0, rank == world - 1)
-        if world > 1:
-            combine_shards(h)
-        return h.peaks()  # sync + D2H of the (combined) table
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        w0 = time.perf_counter()
-        e0.record()
-        for _ in range(steps):
-            fn()
-        e1.record()
-        barrier()
-        wall = time.perf_counter() - w0
-        ms = e0.elapsed_time(e1)
-        # the table read-back is a host sync inside the step; wall and event time agree, keep the larger
-        t = torch.tensor([max(ms / 1e3, wall if args.wall else 0.0)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    for _ in range(max(args.warmup, 3)):
-        step_device()
-    h.reset_stats()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    t_dev = timed(step_device, args.steps)
-    clocks = sampler.stop() if rank == 0 else None
-    st = h.stats()
+    flags = capi.FLAG_NO_PRUNE if args.no_prune else 0
+    sb, job_frames = make(wl, total, strong, flags)
+    A = sb.A
+    sampler = ClockSampler(local) if rank == 0 else None
+    t_dev, st, clocks = sb.run_device(args.steps, args.warmup, sampler, args.wall)
     launches = torch.tensor([st["kernel_launches"]], device=dev, dtype=torch.int64)
     if world > 1:
         dist.all_reduce(launches)
-    sa_step = float(frames) * CHANNELS * A * world
+    sa_step = float(job_frames) * wl["C"] * A
     value = sa_step * args.steps / t_dev / 1e9
     surv = st["points_evaluated"] / max(1, st["points_total"])
-
-    # ---- e2e: pinned host buffer through phaserot_sweep (H2D + table D2H inside the timed region)
-    xh = torch.empty((frames, CHANNELS), dtype=torch.float32, pin_memory=True)
-    xh.copy_(x)
-    torch.cuda.synchronize()
-    he = capi.Phaserot(mode=capi.MODE_CLI, n_channels=CHANNELS, blksiz=BLKSIZ, subsample=args.subsample, device=local,
-                       flags=capi.FLAG_NO_PRUNE if args.no_prune else 0)
-    if world > 1:
-        he.set_stream(stream.cuda_stream)  # the upload, the sweep and the all-reduce are ordered on one stream
-
-    def step_e2e():
-        he.reset()
-        if world == 1:
-            he.sweep((xh.data_ptr(), frames))
-        else:
-            # shard semantics need history: upload then shard call (H2D still inside the step)
-            x.copy_(xh, non_blocking=True)
-            he.sweep_shard_device(x.data_ptr(), frames, hist_ptr, rank == 0, rank == world - 1)
-            combine_shards(he)
-        he.peaks()
-
-    for _ in range(2):
-        step_e2e()
-    e2e_steps = max(2, min(args.steps, 5))
-    barrier()
-    w0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_e2e()
-    barrier()
-    t_e2e = torch.tensor([time.perf_counter() - w0], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t_e2e, op=dist.ReduceOp.MAX)
-    e2e_value = sa_step * e2e_steps / float(t_e2e.item()) / 1e9
-    he.close()
-    del xh
-
-    # ---- roofline leg: per-kernel CUDA-event times of one more step (not part of `value`)
-    h.set_profiling(True)
-    step_device()
-    kt = h.kernel_times()
-    h.set_profiling(False)
-    conv = kt["fftconv_filter"]
-    alg_bytes = 4.0 * frames * CHANNELS  # per rank, per pass (SURVEY 8d: 4 B per input sample)
-    peak, peak_src = measured_hbm_peak()
-    achieved = alg_bytes / (conv["ms"] * 1e-3) / 1e9 if conv["ms"] > 0 else 0.0
     step_ms = 1e3 * t_dev / args.steps
-    kshare = {k: round(v["ms"], 4) for k, v in kt.items() if v["launches"]}
 
-    # ---- secondary legs (rank 0, N=1): the other two callers of the path.  Not part of `value`.
+    e2e_steps = max(2, min(args.steps, 5))
+    t_e2e = sb.run_e2e(e2e_steps)
+    e2e_value = sa_step * e2e_steps / t_e2e / 1e9
+
+    kt = sb.kernel_times()
+    alg_bytes = 4.0 * sb.frames * wl["C"]  # per rank, per pass (4 B per input sample)
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    roof = roofline_of(kt, alg_bytes, step_ms, sb.frames, wl, sm_mhz) if rank == 0 else None
+
+    # ---- the other scaling view and BASELINE config 5, measured in the same run at every N (objects on the line)
     extra = {}
-    if world == 1 and not args.no_extra:
-        extra = secondary_legs(torch, capi, dev, local, x, frames, peak)
+    if not args.no_strong and args.config != "5" and args.scaling != "strong":
+        if world == 1:
+            extra["strong"] = {"value": value, "ms_per_step": step_ms, "note": "N = 1: identical to the headline run"}
+        else:
+            ss, jf = make(wl, total, True, flags)
+            t, _, _ = ss.run_device(args.steps, args.warmup)
+            te = ss.run_e2e(e2e_steps)
+            k2 = ss.kernel_times()
+            extra["strong"] = {"value": float(jf) * wl["C"] * A * args.steps / t / 1e9, "ms_per_step": 1e3 * t / args.steps,
+                               "e2e_value": float(jf) * wl["C"] * A * e2e_steps / te / 1e9, "e2e_ms_per_step": 1e3 * te / e2e_steps,
+                               "kernels_ms_rank0": {k: round(v["ms"], 4) for k, v in k2.items() if v["launches"]}}
+            ss.close()
+        extra["strong"].update({"unit": "Gsample-angles/s", "scaling": "strong",
+                                "workload": f"ONE {wl['seconds']:g} s stereo file cut on the FFT segment grid into {world} sample-range shard(s), "
+                                            "one per GPU, NCCL max all-reduce of the table (north_star's >= 7x at 8 GPUs is about this)"})
+    if not args.no_config5 and args.config != "5":
+        w5 = dict(WORKLOADS["config5"])
+        s5 = 2 * (16384 - 8192)
+        tot5 = int(w5["seconds"] * w5["sr"])
+        tot5 -= tot5 % s5
+        c5, jf = make(w5, tot5, True, 0)
+        st5 = max(2, min(args.steps, 3))
+        t, stt, _ = c5.run_device(st5, 2)
+        k5 = c5.kernel_times()
+        ms5 = 1e3 * t / st5
+        peak, _ = measured_hbm_peak()
+        extra["config5"] = {"value": float(jf) * w5["C"] * c5.A * st5 / t / 1e9, "unit": "Gsample-angles/s", "ms_per_step": ms5, "scaling": "strong",
+                            "workload": f"{w5['label']}, {w5['seconds']:g} s ({4.0 * jf * w5['C'] / 1e9:.1f} GB), 0.01 deg grid (18000 angles), blksiz 32768, "
+                                        f"cut into {world} sample-range shard(s), device resident",
+                            "hbm_frac_algorithmic_whole_step": 4.0 * jf * w5["C"] / world / (ms5 * 1e-3) / 1e9 / peak,
+                            "kernels_ms_rank0": {k: round(v["ms"], 4) for k, v in k5.items() if v["launches"]},
+                            "survivor_fraction": stt["points_evaluated"] / max(1, stt["points_total"])}
+        c5.close()
+
+    # ---- secondary legs (rank 0, N=1): the other callers of the path, other inputs, the reference grid.  Not part of `value`.
+    if world == 1 and not args.no_extra and args.config != "5":
+        peak, _ = measured_hbm_peak()
+        extra.update(secondary_legs(torch, capi, dev, local, sb.x, sb.frames, peak))
+        extra["inputs"] = input_legs(torch, capi, dev, local, sb.x, sb.frames, step_ms)
+        extra["same_grid"] = same_grid_leg(torch, capi, dev, local, sb.x, args.ref_seconds)
 
     line = None
     if rank == 0:
@@ -593,40 +733,133 @@ def gpu_main(args):
                 cpu = {"value": r["value"], "unit": r["unit"], "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
             except Exception as ex:  # the oracle build is test infrastructure; never fatal for the GPU line
                 cpu = {"value": None, "unit": "Gsample-angles/s", "cores": 0, "kind": "reference", "sample": f"unavailable: {ex}"}
-        traffic = None
+        if cpu and cpu.get("value") and "same_grid" in extra:
+            extra["same_grid"]["vs_cpu_baseline"] = {"device_resident": extra["same_grid"]["value"] / cpu["value"], "e2e": extra["same_grid"]["e2e_value"] / cpu["value"],
+                                                      "same_config": True}
+        if "plugin" in extra and world == 1 and not args.no_cpu:
+            extra["plugin"]["cpu_baseline"] = plugin_cpu_baseline()
         tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-        if os.path.exists(tpath):
+        if os.path.exists(tpath) and args.config != "5":
             try:
-                traffic = json.load(open(tpath)).get("fftconv_filter_dram_bytes_per_launch")
+                roof["traffic"] = json.load(open(tpath)).get("fftconv_filter_dram_bytes_per_launch")
             except Exception:
-                traffic = None
+                pass
+        cfg = workload_config(args, wl, sb.frames, world, strong)
         line = {
             "metric": "min-peak theta sweep throughput", "value": value, "unit": "Gsample-angles/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": step_ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(args),
+            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": cfg,
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": "Gsample-angles/s", "h2d_bytes_per_step": int(frames * CHANNELS * 4 * world),
+            "e2e": {"value": e2e_value, "unit": "Gsample-angles/s", "h2d_bytes_per_step": int(job_frames * wl["C"] * 4),
                     "host_numa_binding": ("rank bound to %d GPU-local CPUs" % len(numa)) if numa else "none",
-                    "d2h_bytes_per_step": int((CHANNELS * A + CHANNELS) * 4 * world), "steps": e2e_steps,
-                    "ms_per_step": 1e3 * float(t_e2e.item()) / e2e_steps},
+                    "d2h_bytes_per_step": int((wl["C"] * A + wl["C"]) * 4 * world), "steps": e2e_steps,
+                    "ms_per_step": 1e3 * t_e2e / e2e_steps,
+                    "path": "phaserot_sweep (N = 1) / phaserot_sweep_shard (N > 1): pinned host buffer, chunked upload overlapped with the sweep"},
             "gpu_launches": int(launches.item()),
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                         "kernel": "fftconv_kernel<EPI_POINTS>", "peak_source": peak_src,
-                         "algorithmic_bytes_per_step_per_gpu": alg_bytes, "kernel_ms_per_step": conv["ms"], "launches_per_step": conv["launches"],
-                         "kernel_share_of_step": conv["ms"] / step_ms if step_ms else None,
-                         "whole_step_frac": alg_bytes / (step_ms * 1e-3) / 1e9 / peak,
-                         "all_kernels_ms": kshare},
-            "pruning": {"enabled": not args.no_prune, "survivor_fraction": surv, "points_per_step_per_gpu": st["points_total"] // max(1, args.steps)},
+            "roofline": roof,
+            "pruning": {"enabled": not args.no_prune, "survivor_fraction": surv, "points_per_step_per_gpu": st["points_total"] // max(1, args.steps),
+                        "dense_repeats": st["dense_repeats"]},
             "cpu_baseline": cpu,
         }
         line.update(extra)
-    h.close()
+    sb.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:
         print(json.dumps(line))
+
+
+def input_legs(torch, capi, dev, local, prog, frames, programme_ms):
+    """The sweep's cost as a function of the INPUT (exact pruning makes the time depend on how many samples lie near
+    the hull of the (x_d, H) point set): the same 1 h / 0.1 degree pass on config-1 two-sine material, on a pure sine
+    (constant envelope: the worst case, every sample is on the hull) and on the programme with pruning switched off."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import input_legs as IL
+    out = {}
+    for name, (x, fl) in IL.materials(torch, dev, frames, SR, prog).items():
+        if name == "programme":
+            continue
+        r, _ = IL.run_leg(torch, capi, x.contiguous(), frames, BLKSIZ, SUBSAMPLE, fl, steps=3, device=local)
+        r["vs_programme_leg"] = r["ms_per_step"] / programme_ms
+        out[name] = r
+        del x
+    out["note"] = ("stereo 48 kHz, 1 h, 1800 angles, device resident, steady state of a handle (first_call_ms includes the one-off dense-mode repeat); "
+                   "every table is bit-identical to brute force (tests/test_gpu_round2.py, tools/input_legs.py --check)")
+    return out
+
+
+def same_grid_leg(torch, capi, dev, local, prog, ref_seconds):
+    """The GPU arm on exactly the reference arm's configuration: ref_seconds of the same programme, the reference's own
+    0.5 degree grid (360 indices).  Rates on the headline's 0.1 degree grid are ~5x higher for the same time because exact
+    pruning makes the GPU time almost independent of the angle count; this object is the like-for-like anchor."""
+    frames = int(ref_seconds * SR)
+    x = prog[:frames].contiguous()
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    with capi.Phaserot(mode=capi.MODE_CLI, n_channels=CHANNELS, blksiz=BLKSIZ, subsample=2, device=local) as h:
+        h.set_stream(torch.cuda.current_stream().cuda_stream)
+        for _ in range(3):
+            h.reset()
+            h.sweep_device(x.data_ptr(), frames)
+            h.peaks()
+        e0, e1 = ev(), ev()
+        n = 10
+        e0.record()
+        for _ in range(n):
+            h.reset()
+            h.sweep_device(x.data_ptr(), frames)
+            h.peaks()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+    xh = torch.empty((frames, CHANNELS), dtype=torch.float32, pin_memory=True)
+    xh.copy_(x)
+    torch.cuda.synchronize()
+    with capi.Phaserot(mode=capi.MODE_CLI, n_channels=CHANNELS, blksiz=BLKSIZ, subsample=2, device=local) as h:
+        for _ in range(2):
+            h.reset()
+            h.sweep((xh.data_ptr(), frames))
+        t0 = time.perf_counter()
+        for _ in range(5):
+            h.reset()
+            h.sweep((xh.data_ptr(), frames))
+            h.peaks()
+        dt = (time.perf_counter() - t0) / 5
+    sa = float(frames) * CHANNELS * 360
+    return {"value": sa / (ms * 1e-3) / 1e9, "e2e_value": sa / dt / 1e9, "unit": "Gsample-angles/s", "ms_per_step": ms, "e2e_ms_per_step": 1e3 * dt,
+            "workload": f"{ref_seconds:g} s of the stereo 48 kHz programme, reference grid 0.5 deg (360 indices), blksiz {BLKSIZ}: the reference arm's configuration"}
+
+
+def plugin_cpu_baseline():
+    """BASELINE.md row 2 on the host cores: the reference plugin built from the unmodified source (oracle/_ref/phaserotate_ref.so,
+    stand-in float FFT) and this repository's LV2 BINARY, both driven through the same minimal LV2 host (oracle/lv2_harness.c)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    try:
+        import oracle_lib as O
+        from phaserotate.lv2_b200 import build as B
+        rng = np.random.default_rng(42)
+        out = {}
+        n_small, n_bulk = 1024 * 2000, 600 * SR
+        xs = (0.25 * rng.standard_normal(n_small)).astype(np.float32)[None, :]
+        xb = (0.25 * rng.standard_normal(n_bulk)).astype(np.float32)[None, :]
+        ref_so = os.path.join(O.REF_DIR, "phaserotate_ref.so")
+        our_so = os.path.join(B.BIN_DIR, "phaserotate_cuda.so")
+        for tag, so in (("reference_cpu", ref_so), ("cuda_lv2_binary", our_so)):
+            if not os.path.exists(so):
+                out[tag] = {"unavailable": os.path.relpath(so, ROOT)}
+                continue
+            O.lv2_render(so, xs[:, :1024 * 200], 48000.0, 1024, 90.0)  # warm
+            _, _, dt = O.lv2_render(so, xs, 48000.0, 1024, 90.0)
+            _, _, db = O.lv2_render(so, xb, 48000.0, n_bulk, 90.0)
+            out[tag] = {"us_per_1024_frame_call": 1e6 * dt / 2000, "msamples_per_s_1024": n_small / dt / 1e6,
+                        "bulk_ms_per_600s_call": 1e3 * db, "msamples_per_s_bulk": n_bulk / db / 1e6}
+        out["cores"] = 1
+        out["kind"] = "reference"
+        out["sample"] = "mono 48 kHz white noise, angle 90 deg: 2000 run() calls of 1024 frames, and one 600 s call; seconds spent inside run()"
+        return out
+    except Exception as ex:
+        return {"unavailable": str(ex)}
 
 
 def main():
@@ -635,7 +868,12 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--seconds", type=float, default=3600.0, help="audio seconds per GPU (default: the 1-hour headline workload)")
+    ap.add_argument("--seconds", type=float, default=0.0, help="audio seconds (per GPU for weak scaling, in total for strong); default: the workload's 1 hour")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: one --seconds stretch per GPU (default); strong: ONE --seconds file cut into one shard per GPU")
+    ap.add_argument("--config", default="headline", choices=["headline", "5"], help="5: BASELINE config 5 (8 ch, 192 kHz, 1 h, 0.01 deg, blksiz 32768), strong scaling")
+    ap.add_argument("--no-strong", action="store_true", help="skip the `strong` object (the 1 h file cut across the ranks) of a weak-scaling run")
+    ap.add_argument("--no-config5", action="store_true", help="skip the `config5` object")
     ap.add_argument("--subsample", type=int, default=SUBSAMPLE)
     ap.add_argument("--ref-seconds", type=float, default=240.0, help="bounded CPU sample for the reference arm")
     ap.add_argument("--no-prune", action="store_true", help="evaluate every sample at every angle")

@@ -126,7 +126,16 @@ PHASEROT_API int phaserot_set_stream (phaserot_t* h, void* cuda_stream);
  *
  * Results accumulate (max) into the handle's peak table exactly like
  * PhaseRotate::_peak; read them with phaserot_peak()/phaserot_peaks().
- * Synchronous: the table is final when the call returns. */
+ * Synchronous: the table is final when the call returns.
+ *
+ * Cost model: exact pruning drops every sample that cannot raise any angle's
+ * running maximum; what survives goes on a list sized for programme material
+ * (1/32 of a launch's samples).  Few-tone or constant-envelope input, where most
+ * samples lie on the hull of the (x_d, H) point set, overflows it: the pass is
+ * then repeated once in dense mode (launches sized to the list, and every
+ * survivor evaluated only at the few angles it can still raise), the handle
+ * stays in dense mode while the material needs it, and the table is the same
+ * bit for bit either way (phaserot_stats_t.dense_repeats counts the repeats). */
 PHASEROT_API int phaserot_sweep (phaserot_t* h, const float* interleaved, uint64_t n_frames,
                                  int ang_start, int ang_end, int ang_stride, int chn);
 
@@ -316,6 +325,7 @@ typedef struct phaserot_stats {
 	uint64_t points_evaluated; /* pairs that survived pruning and were evaluated at every angle */
 	uint64_t h2d_bytes;
 	uint64_t d2h_bytes;
+	uint64_t dense_repeats;    /* passes repeated in dense mode because a survivor list overflowed (see phaserot_sweep) */
 } phaserot_stats_t;
 PHASEROT_API int phaserot_get_stats (phaserot_t* h, phaserot_stats_t* out);
 PHASEROT_API int phaserot_reset_stats (phaserot_t* h);

@@ -43,7 +43,7 @@ class Cfg(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("points_total", C.c_uint64), ("points_evaluated", C.c_uint64),
-                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64), ("dense_repeats", C.c_uint64)]
 
 
 NKERNELS = 7

@@ -77,6 +77,8 @@ struct ConvParams {
 	float2*       list;         // [n_chan][list_stride]
 	long long     list_stride;
 	unsigned*     count;        // [n_chan]
+	unsigned      list_cap;     // points that fit a channel's list; survivors beyond it are dropped and *overflow is set
+	unsigned*     overflow;     // [1] the pass is incomplete: the host repeats it in dense mode (launches sized to the list)
 	const float*  thr2;         // [n_chan] squared filter radius (thr_mode < 0: written by threshold_kernel)
 	unsigned*     rawpeak;      // [n_chan] bits of max |x|
 	// EPI_POINTS, thr_mode >= 0: the filter radius is derived inside the kernel from the
@@ -99,11 +101,6 @@ struct ConvParams {
 	float*        out_inter;    // EPI_RENDER: interleaved destination [out_frames][C] instead of `out` (fused CLI render)
 	long long     out_frames;
 	int           out_compact;  // EPI_HILBERT: segment j of the launch writes its V outputs at out[8 + j V ..) (true-peak staging)
-	// launched as thread-block clusters of `pair_sync` CTAs = the CTAs that walk the channels of one
-	// stretch of interleaved frames: they meet once per segment (split arrive / wait), so that none
-	// runs more than one segment ahead and every sector of the stretch is fetched from HBM once
-	int           pair_sync;
-	int           prefetch;     // 1: pull the next segment towards L2 while the current one is transformed
 };
 
 // Segment input loaders: z[n0 + idx] for the first forward pass and the direct
@@ -196,17 +193,57 @@ __device__ __forceinline__ unsigned lanemask_lt ()
 // (channel, segment) pairs.
 // ---------------------------------------------------------------------------
 // warp-aggregated append of up to two points per lane to the survivor list
-__device__ __forceinline__ void append_points (float2* lst, unsigned* cnt, bool k0, float2 p0, bool k1, float2 p1, unsigned lt, int lane)
+struct ListDst {
+	float2*   lst;
+	unsigned* cnt;
+	unsigned  cap;
+	unsigned* ovf;
+};
+__device__ __forceinline__ void append_points (const ListDst& d, bool k0, float2 p0, bool k1, float2 p1, unsigned lt, int lane)
 {
 	const unsigned b0 = __ballot_sync (0xffffffffu, k0);
 	const unsigned b1 = __ballot_sync (0xffffffffu, k1);
 	if (b0 | b1) {
 		const int n0   = __popc (b0);
 		unsigned  base = 0;
-		if (lane == 0) base = atomicAdd (cnt, (unsigned)(n0 + __popc (b1)));
+		if (lane == 0) {
+			base = atomicAdd (d.cnt, (unsigned)(n0 + __popc (b1)));
+			if (base + (unsigned)(n0 + __popc (b1)) > d.cap) *d.ovf = 1u; // rare: the host repeats the pass (dense mode)
+		}
 		base = __shfl_sync (0xffffffffu, base, 0);
-		if (k0) lst[base + __popc (b0 & lt)] = p0;
-		if (k1) lst[base + n0 + __popc (b1 & lt)] = p1;
+		const unsigned i0 = base + __popc (b0 & lt), i1 = base + n0 + __popc (b1 & lt);
+		if (k0 && i0 < d.cap) d.lst[i0] = p0;
+		if (k1 && i1 < d.cap) d.lst[i1] = p1;
+	}
+}
+
+// The same for the eight samples a lane holds of one block of four strides: ONE reservation per warp
+// and block.  On material where most samples survive (dense mode) the list counter is the
+// bottleneck of the kernel: same-address atomics retire at ~1 per ns.
+__device__ __forceinline__ void append_points4 (const ListDst& d, const bool (&k0)[4], const float2 (&p0)[4], const bool (&k1)[4], const float2 (&p1)[4], unsigned lt, int lane)
+{
+	unsigned b[8];
+	int      n = 0;
+#pragma unroll
+	for (int kk = 0; kk < 4; ++kk) {
+		b[2 * kk]     = __ballot_sync (0xffffffffu, k0[kk]);
+		b[2 * kk + 1] = __ballot_sync (0xffffffffu, k1[kk]);
+		n += __popc (b[2 * kk]) + __popc (b[2 * kk + 1]);
+	}
+	unsigned base = 0;
+	if (lane == 0) {
+		base = atomicAdd (d.cnt, (unsigned)n);
+		if (base + (unsigned)n > d.cap) *d.ovf = 1u;
+	}
+	base = __shfl_sync (0xffffffffu, base, 0);
+#pragma unroll
+	for (int kk = 0; kk < 4; ++kk) {
+		const unsigned i0 = base + __popc (b[2 * kk] & lt);
+		base += __popc (b[2 * kk]);
+		const unsigned i1 = base + __popc (b[2 * kk + 1] & lt);
+		base += __popc (b[2 * kk + 1]);
+		if (k0[kk] && i0 < d.cap) d.lst[i0] = p0[kk];
+		if (k1[kk] && i1 < d.cap) d.lst[i1] = p1[kk];
 	}
 }
 
@@ -330,8 +367,7 @@ __device__ __forceinline__ void epilogue (const float2 (&w)[32], float* xch, uin
 	const int xbase = warp ? (warp - 1) * 32 : 15 * 32 - 1;
 	if (EPI == EPI_POINTS) {
 		float          thr2   = xch[kXchFloats + 4 + kRedThr]; // parked in shared memory by the kernel prologue
-		float2*        lst    = p.list + (long long)cx.c * p.list_stride;
-		unsigned*      cnt    = p.count + cx.c;
+		const ListDst  dst    = { p.list + (long long)cx.c * p.list_stride, p.count + cx.c, p.list_cap, p.overflow };
 		const unsigned lt     = lanemask_lt ();
 		float          rawmax = cx.rawmax;
 		if (p.boot_beta > 0.f) {
@@ -380,10 +416,13 @@ __device__ __forceinline__ void epilogue (const float2 (&w)[32], float* xch, uin
 					any    = any || k0[kk] || k1[kk];
 				}
 				if (__any_sync (0xffffffffu, any)) { // one vote per eight samples; survivors are a fraction of a percent
+					float2 q0[4], q1[4];
 #pragma unroll
 					for (int kk = 0; kk < 4; ++kk) {
-						append_points (lst, cnt, k0[kk], make_float2 (zd[kk].x, pv[kk]), k1[kk], make_float2 (zd[kk].y, w[kb + kk].x), lt, lane);
+						q0[kk] = make_float2 (zd[kk].x, pv[kk]);
+						q1[kk] = make_float2 (zd[kk].y, w[kb + kk].x);
 					}
+					append_points4 (dst, k0, q0, k1, q1, lt, lane);
 				}
 			}
 		} else {
@@ -391,7 +430,7 @@ __device__ __forceinline__ void epilogue (const float2 (&w)[32], float* xch, uin
 				if (ok) rawmax = fmaxf (rawmax, fmaxf (fabsf (zd.x), fabsf (zd.y)));
 				const bool k0 = in && fmaf (p0.x, p0.x, p0.y * p0.y) >= thr2;
 				const bool k1 = in && fmaf (p1.x, p1.x, p1.y * p1.y) >= thr2;
-				if (__any_sync (0xffffffffu, k0 || k1)) append_points (lst, cnt, k0, p0, k1, p1, lt, lane);
+				if (__any_sync (0xffffffffu, k0 || k1)) append_points (dst, k0, p0, k1, p1, lt, lane);
 			});
 		}
 		cx.rawmax = rawmax;
@@ -581,7 +620,6 @@ __global__ void __launch_bounds__ (kConvThreads, 1) fftconv_kernel (const ConvPa
 	const int c = p.chan0 + ci;
 	bool prev_inside = false;
 	for (int si = s_begin; si < s_end; ++si) {
-		if (p.pair_sync) asm volatile ("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); // "I have started segment si"
 
 		const long long seg = p.seg0 + si * p.seg_stride + (p.seg_jitter ? (long long)(((unsigned)si * 2654435761u >> 8) % (unsigned)p.seg_stride) : 0);
 		const long long n0  = seg * p.V - p.Lh; // complex stream index of local index 0
@@ -593,26 +631,9 @@ __global__ void __launch_bounds__ (kConvThreads, 1) fftconv_kernel (const ConvPa
 				spectrum_only (sm, xch, p.tw1, p.tw2, p.scratch + (size_t)blockIdx.x * (kM / 2), tid, EdgeLoader { p.inter, p.hist, p.n_frames, 2 * (n0 - p.V), p.C, c, p.hist_frames });
 			}
 		}
-		if (p.prefetch && si + 1 < s_end && lane == 0 && (SRC == SRC_PLANE || ci == 0)) {
-			// pull the new part of the next segment towards L2 while this one is
-			// transformed: one bulk prefetch per warp, 16 pieces
-			const long long nn0 = n0 + p.seg_stride * p.V + (p.seg_stride == 1 ? p.Lh : 0);
-			const long long npt = p.seg_stride == 1 ? p.V : kM;
-			const char*     pf;
-			long long       nbytes;
-			if (SRC == SRC_PLANE) {
-				pf     = reinterpret_cast<const char*> (p.plane + (long long)c * p.plane_stride + p.padf + nn0);
-				nbytes = npt * (long long)sizeof (float2);
-			} else {
-				pf     = reinterpret_cast<const char*> (p.inter + 2 * nn0 * p.C);
-				nbytes = (nn0 >= 0 && 2 * (nn0 + npt) <= p.n_frames) ? npt * 2 * p.C * (long long)sizeof (float) : 0;
-			}
-			if (nbytes > 0) {
-				const unsigned piece = (unsigned)(nbytes >> 4) & ~15u;
-				const char*    a     = reinterpret_cast<const char*> (reinterpret_cast<uintptr_t> (pf) & ~(uintptr_t)15) + (size_t)(tid >> 5) * piece;
-				asm volatile ("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(piece) : "memory");
-			}
-		}
+		// (No L2 prefetch of the next segment: a cp.async.bulk.prefetch.L2 of the stretch one
+		// segment ahead made the long launches read 1.26x their bytes from HBM - the lines were
+		// fetched, evicted and fetched again - and was 1 % slower than plain loads; r02 traffic probe.)
 
 		// local bounds of the output regions (clamped to the segment)
 		cx.c     = c;
@@ -641,7 +662,6 @@ __global__ void __launch_bounds__ (kConvThreads, 1) fftconv_kernel (const ConvPa
 				run_segment<EPI, NP> (sm, xch, tb, p, tid, lane, cx, InterNLoader { p.inter + 2 * n0 * p.C + c, p.C }, reuse);
 			}
 		}
-		if (p.pair_sync) asm volatile ("barrier.cluster.wait.aligned;" ::: "memory"); // every sibling has started segment si
 	}
 
 	if (EPI == EPI_POINTS && s_begin < s_end) {
@@ -779,14 +799,15 @@ constexpr int kSweepTile = 256; // points per tile
 
 template <int R>
 __global__ void __launch_bounds__ (256) sweep_kernel (const float2* __restrict__ list, long long list_stride,
-                                                       const unsigned* __restrict__ count, int chan0,
+                                                       const unsigned* __restrict__ count, unsigned cap, int skip_overflowed, int chan0,
                                                        const float2* __restrict__ cs, int A,
                                                        unsigned* __restrict__ peaks, int peaks_stride,
                                                        unsigned long long* __restrict__ n_eval)
 {
 	__shared__ __align__ (16) float2 tile[kSweepTile];
 	const int       c    = chan0 + blockIdx.z;
-	const unsigned  n    = count[c];
+	if (skip_overflowed && count[c] > cap) return;  // the pass is flagged and will be repeated in dense mode: do not brute-force a full list first
+	const unsigned  n    = min (count[c], cap); // (bootstrap wave: the counter may run past its small capacity, the excess was dropped)
 	if (blockIdx.x * kSweepTile >= n) return; // most launches see a few dozen survivors: nothing for this CTA
 	const float2*   pts  = list + (long long)c * list_stride;
 	const int       a0   = blockIdx.y * (blockDim.x * R) + threadIdx.x;
@@ -860,6 +881,147 @@ __global__ void threshold_kernel (const unsigned* __restrict__ peaks, int peaks_
 			thr2[c] = (m * m) * 0.99999f;
 			if (reset_count) count[c] = 0;
 		}
+	}
+}
+
+// ---------------------------------------------------------------------------
+// Dense mode (long survivor lists: few-tone or constant-envelope material, where
+// most samples lie on or near the hull of the point set {(x_d, H)} and the
+// global radius filter keeps them).  A point p = r (cos phi, sin phi) gives
+//     y_j = ca_j x + sa_j h = r cos (alpha_j - phi),   alpha_j = -j * step (grid index j)
+// so it can raise the running peak of grid angle j only if
+//     r |cos (alpha_j - phi)| >= T_j   (T_j <= peak[j], any earlier value of it).
+// The grid is cut into kSectors sectors of equal width; sector_thr_kernel takes
+// T_s = min over the swept angles of sector s of the running peaks, and
+// sweep_window_kernel (one thread per point) visits only the sectors within
+// reach of the global threshold, tests the sector bound
+//     r cos (dist (phi, sector s)) >= T_s
+// and evaluates only the angles of a passing sector with |alpha_j - phi| <=
+// acos (T_s / r) - with the SAME fp32 expression as sweep_kernel, so the table is
+// bit-identical to brute force.  Interior points (most of a two-tone signal's
+// survivors) cost a few sector tests, points of a constant-envelope signal a
+// handful of angles instead of all of them.  Points that still need more than
+// kWideEvals evaluations go to a second list for sweep_kernel (angles in lanes).
+// All margins err towards evaluating: 4e-6 relative on T / r (the fp32
+// evaluation of y and r is good to ~3e-7), 2e-5 rad + one grid step on every
+// angular bound (atan2f / acosf / the LUT's own rounding are below 2e-6 rad).
+// ---------------------------------------------------------------------------
+constexpr int kSectors   = 60;  // divides 180 * S for every S
+constexpr int kWideEvals = 768;
+
+// sec[c][s] = min over slots k with grid index in sector s of peaks[c][k]  (+inf: nothing swept there)
+__global__ void __launch_bounds__ (64) sector_thr_kernel (const unsigned* __restrict__ peaks, int peaks_stride, const int* __restrict__ slot_of, int MS, int chan0,
+                                                          float* __restrict__ sec)
+{
+	const int c = chan0 + blockIdx.y, s = blockIdx.x, G = MS / kSectors;
+	float     m = __int_as_float (0x7f800000);
+	for (int j = s * G + threadIdx.x; j < (s + 1) * G; j += blockDim.x) {
+		const int k = slot_of[j];
+		if (k >= 0) m = fminf (m, __uint_as_float (peaks[(long long)c * peaks_stride + k]));
+	}
+	__shared__ float red[2];
+	for (int o = 16; o; o >>= 1) m = fminf (m, __shfl_xor_sync (0xffffffffu, m, o));
+	if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+	__syncthreads ();
+	if (threadIdx.x == 0) sec[c * kSectors + s] = fminf (red[0], red[1]);
+}
+
+struct WinParams {
+	const float2*   list;
+	long long       list_stride;
+	const unsigned* count;
+	unsigned        cap;
+	int             chan0;
+	const float2*   cs;       // [A] (ca, sa) per slot
+	const int*      slot_of;  // [MS] grid index -> slot, -1 = not swept
+	int             MS;
+	const float*    sec;      // [C][kSectors]
+	unsigned*       peaks;
+	int             peaks_stride;
+	float2*         wide;     // [C][wide_stride] points left to sweep_kernel
+	long long       wide_stride;
+	unsigned*       wide_count; // [C]
+	unsigned long long* n_eval; // statistics: point-angle evaluations / A
+	unsigned long long* n_listed; // statistics: points on the lists of this sweep
+	int             A;
+};
+
+// acos (q) <= sqrt (2 u) (1 + 0.12 u), u = 1 - q in [0, 1]  (series sqrt(2u)(1 + u/12 + 3u^2/160 + ...); 1.584 >= pi/2 at u = 1)
+__device__ __forceinline__ float acos_upper (float q)
+{
+	const float u = fmaxf (1.f - q, 0.f);
+	return sqrtf (2.f * u) * fmaf (0.12f, u, 1.f) * 1.000001f;
+}
+
+__global__ void __launch_bounds__ (256) sweep_window_kernel (const WinParams p)
+{
+	const int      c = p.chan0 + blockIdx.y;
+	const unsigned n = min (p.count[c], p.cap);
+	const float    step = 3.14159265358979f / (float)p.MS, inv_step = (float)p.MS / 3.14159265358979f;
+	const int      G = p.MS / kSectors;
+	const float    inv_G = 1.f / (float)G;
+	const float*   sec = p.sec + c * kSectors;
+	unsigned*      pk  = p.peaks + (long long)c * p.peaks_stride;
+	// global threshold = the smallest sector threshold (every running peak is at least that)
+	__shared__ float tg_s;
+	if (threadIdx.x < 32) {
+		float m = fminf (sec[threadIdx.x], threadIdx.x + 32 < kSectors ? sec[threadIdx.x + 32] : __int_as_float (0x7f800000));
+		for (int o = 16; o; o >>= 1) m = fminf (m, __shfl_xor_sync (0xffffffffu, m, o));
+		if (threadIdx.x == 0) tg_s = m;
+	}
+	__syncthreads ();
+	const float tg = tg_s * (1.f - 4e-6f);
+	if (!(tg < __int_as_float (0x7f800000))) return; // no angle swept
+	if (blockIdx.x == 0 && threadIdx.x == 0 && p.n_listed) atomicAdd (p.n_listed, (unsigned long long)n);
+	unsigned long long evals = 0;
+	for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+		const float2 q  = p.list[(long long)c * p.list_stride + i];
+		const float  r2 = fmaf (q.x, q.x, q.y * q.y);
+		if (!(r2 > 0.f)) continue;
+		const float ri = rsqrtf (r2) * (1.f - 1e-6f); // a lower bound of 1 / r: thresholds over r come out low, windows wide
+		// fractional grid index of the direction of the point: alpha = phi (mod pi)  <=>  j = -phi / step (mod MS)
+		const float jc = -atan2f (q.y, q.x) * inv_step;
+		// reach of the global threshold in grid steps
+		const float rg = (acos_upper (tg * ri) + 2e-5f) * inv_step + 1.f;
+		bool        wide = !(2.f * rg + 2.f < (float)p.MS); // (nearly) the whole grid
+		int         done = 0;
+		if (!wide) {
+			const int s_lo = (int)floorf ((jc - rg) * inv_G), s_hi = (int)floorf ((jc + rg) * inv_G);
+			for (int su = s_lo; su <= s_hi && !wide; ++su) {
+				int sm = su % kSectors;
+				if (sm < 0) sm += kSectors;
+				const float qs = sec[sm] * (1.f - 4e-6f) * ri; // T_s / r
+				if (!(qs <= 1.f)) continue;                    // nothing swept in the sector, or its threshold is above r
+				// angular half width within which the point can still reach the sector's threshold
+				const float rs = (acos_upper (qs) + 2e-5f) * inv_step + 1.f;
+				const int   j0 = max (su * G, (int)ceilf (jc - rs)), j1 = min (su * G + G - 1, (int)floorf (jc + rs));
+				if (j1 < j0) continue;                         // the sector lies outside that window
+				done += j1 - j0 + 1;
+				if (done > kWideEvals) {
+					wide = true; // what has been evaluated stays valid (a running maximum); the point is redone whole
+					break;
+				}
+				int jj = j0 % p.MS;
+				if (jj < 0) jj += p.MS;
+				for (int j = j0; j <= j1; ++j) {
+					const int k = p.slot_of[jj];
+					if (++jj == p.MS) jj = 0;
+					if (k < 0) continue;
+					const float2 w = p.cs[k];
+					const float  y = fabsf (fmaf (w.x, q.x, w.y * q.y)); // sweep_kernel's expression
+					if (__float_as_uint (y) > pk[k]) atomicMax (pk + k, __float_as_uint (y));
+				}
+			}
+			evals += (unsigned long long)done;
+		}
+		if (wide) {
+			const unsigned at = atomicAdd (p.wide_count + c, 1u);
+			p.wide[(long long)c * p.wide_stride + at] = q; // the wide list has the capacity of the list itself
+		}
+	}
+	if (p.n_eval) {
+		for (int o = 16; o; o >>= 1) evals += __shfl_xor_sync (0xffffffffu, evals, o);
+		if ((threadIdx.x & 31) == 0 && evals) atomicAdd (p.n_eval, (evals + (unsigned long long)p.A - 1) / (unsigned long long)p.A);
 	}
 }
 
@@ -1022,6 +1184,8 @@ struct TpParams {
 	float2*      list;
 	long long    list_stride;
 	unsigned*    count;
+	unsigned     list_cap;    // as in ConvParams
+	unsigned*    overflow;
 	const float* thr2;
 	unsigned*    rawpeak;
 };
@@ -1053,7 +1217,7 @@ __device__ __forceinline__ float2 tp_interp2 (const float2 (&s)[16], int n)
 }
 
 // survivors of one sample (bit q of `keep` = point q) -> list, one atomic per warp
-__device__ __forceinline__ void tp_append (float2* lst, unsigned* cnt, unsigned keep, const float2 (&pt)[5], int lane)
+__device__ __forceinline__ void tp_append (float2* lst, unsigned* cnt, unsigned cap, unsigned* ovf, unsigned keep, const float2 (&pt)[5], int lane)
 {
 	if (__any_sync (0xffffffffu, keep != 0)) {
 		// exclusive prefix sum of the per-lane survivor counts
@@ -1065,12 +1229,18 @@ __device__ __forceinline__ void tp_append (float2* lst, unsigned* cnt, unsigned 
 			if (lane >= o) inc += v;
 		}
 		unsigned base = 0;
-		if (lane == 31) base = atomicAdd (cnt, (unsigned)inc);
+		if (lane == 31) {
+			base = atomicAdd (cnt, (unsigned)inc);
+			if (base + (unsigned)inc > cap) *ovf = 1u;
+		}
 		base          = __shfl_sync (0xffffffffu, base, 31);
 		unsigned pos  = base + (unsigned)(inc - nk);
 #pragma unroll
 		for (int q = 0; q < 5; ++q) {
-			if (keep & (1u << q)) lst[pos++] = pt[q];
+			if (keep & (1u << q)) {
+				if (pos < cap) lst[pos] = pt[q];
+				++pos;
+			}
 		}
 	}
 }
@@ -1142,7 +1312,7 @@ __global__ void __launch_bounds__ (256, 4) truepeak_kernel (const TpParams p)
 				rmax = fmaxf (rmax, fabsf (pt[q].x));
 				if (fmaf (pt[q].x, pt[q].x, pt[q].y * pt[q].y) >= thr2f && (p.os == 4 || !(q == 2 || q == 4))) keep |= 1u << q;
 			}
-			tp_append (lstf, cntf, keep, pt, lanef);
+			tp_append (lstf, cntf, p.list_cap, p.overflow, keep, pt, lanef);
 		}
 		for (int o = 16; o; o >>= 1) rmax = fmaxf (rmax, __shfl_xor_sync (0xffffffffu, rmax, o));
 		if (lanef == 0 && rmax > 0.f) atomicMax (p.rawpeak + c, __float_as_uint (rmax));
@@ -1210,7 +1380,7 @@ __global__ void __launch_bounds__ (256, 4) truepeak_kernel (const TpParams p)
 			if (in) rawmax = fmaxf (rawmax, fabsf (xr[q]));
 			if (ex && fmaf (pt[q].x, pt[q].x, pt[q].y * pt[q].y) >= thr2 && (p.os == 4 || !(q == 2 || q == 4))) keep |= 1u << q;
 		}
-		tp_append (lst, cnt, keep, pt, lane);
+		tp_append (lst, cnt, p.list_cap, p.overflow, keep, pt, lane);
 	}
 	for (int o = 16; o; o >>= 1) rawmax = fmaxf (rawmax, __shfl_xor_sync (0xffffffffu, rawmax, o));
 	if (lane == 0 && rawmax > 0.f) atomicMax (p.rawpeak + c, __float_as_uint (rawmax));

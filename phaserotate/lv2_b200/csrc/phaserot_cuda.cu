@@ -179,7 +179,6 @@ struct phaserot {
 	phaserot_cfg_t cfg;
 	int            dev   = 0;
 	int            n_sm  = 148;
-	int            pair_sync = 1; // clusters of sibling CTAs on interleaved input (PHASEROT_PAIR_SYNC=0 switches it off)
 	int            C     = 1;
 	int            L     = 0;   // FIR length
 	int            Lh    = 0;   // half taps (odd taps of the FIR)
@@ -203,6 +202,20 @@ struct phaserot {
 	DevBuf d_plane, d_out, d_list, d_stage[2], d_io, d_inter, d_hist;
 	DevBuf d_small; // count[C] | thr2[C] | raw[C] | ramp_len[C] | stats[2 x u64]
 	DevBuf d_cs, d_peaks, d_ramp, d_chancs;
+	// dense mode (long survivor lists, see sweep_window_kernel): grid index -> slot, sector thresholds, wide list
+	DevBuf d_slot, d_sec, d_wide;
+	PinBuf h_slot;
+	bool      dense_mode  = false; // sticky: the last sweep overflowed its survivor list (few-tone / constant-envelope material)
+	long long list_cap    = 0;     // points per channel the list holds
+	// what the pending sweep ran over, for a dense-mode repeat from finish_pending() (device pointers)
+	struct Redo {
+		const float* src = nullptr;
+		long long    n_frames = 0, t_end = 0;
+		bool         first_block = false;
+		const float* hist = nullptr;
+		int          ang_start = 0, ang_end = 0, ang_stride = 1, chn = -1;
+	} redo;
+	uint64_t pend_points = 0; // points examined by the pending sweep (statistics; dense-mode exit test)
 	DevBuf d_tpH; // true-peak staging of the Hilbert branch: [C][tp_stride] floats
 	long long tp_stride = 0;
 	int       OS        = 1; // 1 = digital peak, 2 / 4 = oversampled true-peak
@@ -265,7 +278,9 @@ struct DevGuard {
 };
 
 // d_small: count[64] | thr2[64] | raw[64] | ramp_len[64] | stats[2 x u64] | count of odd launches[64] | r2max[64]
-constexpr size_t kSmallBytes = 6 * 64 * sizeof (int) + 2 * sizeof (unsigned long long);
+// ... | stats[3 x u64: points listed in dense mode, evaluated points, list overflow flag] | count of odd launches[64] | r2max[64] | wide list count[64]
+constexpr size_t kSmallBytes = 7 * 64 * sizeof (int) + 3 * sizeof (unsigned long long);
+static_assert (sizeof (unsigned long long) == 2 * sizeof (unsigned), "d_overflow () + 1 is the unread upper half of the flag word");
 struct ProfScope {
 	phaserot* h;
 	size_t    slot = (size_t)-1;
@@ -313,8 +328,10 @@ float*              d_thr2 (phaserot* h) { return (float*)h->d_small.p + 64; }
 unsigned*           d_raw (phaserot* h) { return (unsigned*)h->d_peaks.p + (size_t)std::max (h->pend_A, 1) * h->C; }
 int*                d_ramplen (phaserot* h) { return (int*)h->d_small.p + 192; }
 unsigned long long* d_stats (phaserot* h) { return (unsigned long long*)((char*)h->d_small.p + 4 * 64 * sizeof (int)); }
-unsigned*           d_count_odd (phaserot* h) { return (unsigned*)((char*)h->d_small.p + 4 * 64 * sizeof (int) + 2 * sizeof (unsigned long long)); }
+unsigned*           d_overflow (phaserot* h) { return (unsigned*)(d_stats (h) + 2); }
+unsigned*           d_count_odd (phaserot* h) { return (unsigned*)((char*)h->d_small.p + 4 * 64 * sizeof (int) + 3 * sizeof (unsigned long long)); }
 unsigned*           d_r2max (phaserot* h) { return d_count_odd (h) + 64; }
+unsigned*           d_wide_count (phaserot* h) { return d_r2max (h) + 64; }
 
 int
 upload_tables (phaserot* h)
@@ -368,7 +385,6 @@ fill_conv_common (phaserot* h, ConvParams& p)
 	p.G1           = (const float2*)h->d_G1.p;
 	p.scratch      = (float4*)h->d_scratch.p;
 	p.seg_stride   = 1;
-	p.prefetch     = getenv ("PHASEROT_PREFETCH") ? atoi (getenv ("PHASEROT_PREFETCH")) : 1;
 }
 
 // Function attributes are per device (per context): phaserot_create() sets them
@@ -387,25 +403,35 @@ set_conv_attr ()
 	return PHASEROT_OK;
 }
 
+// Only the kernels a handle of this shape can launch are touched: setting an
+// attribute loads the kernel's code (CUDA loads modules lazily), and a CLI run on
+// a 48 kHz file needs three of the twenty-odd kernels in the library - the rest
+// would only add to the process start-up time.
+enum {
+	KA_POINTS = 1 << 0, KA_RENDER_INTER = 1 << 1, KA_RENDER_PLANE = 1 << 2, KA_HILBERT = 1 << 3, // x 2 tap partitions: shifted by 4
+	KA_FIR_STREAM = 1 << 8
+};
 int
-set_device_attrs (int dev) // caller holds g_create_lock and has made `dev` current
+set_device_attrs (int dev, bool plugin, int NP, int OS) // caller holds g_create_lock and has made `dev` current
 {
-	static std::vector<char> done;
-	if ((size_t)dev < done.size () && done[(size_t)dev]) {
-		return PHASEROT_OK;
-	}
+	static std::vector<unsigned> done;
+	if (done.size () <= (size_t)dev) done.resize ((size_t)dev + 1, 0u);
+	unsigned want = plugin ? (KA_RENDER_PLANE | KA_FIR_STREAM) : (KA_RENDER_INTER | (OS > 1 ? KA_HILBERT : KA_POINTS));
+	if (NP == 2) want = ((want & 0xf) << 4) | (want & ~0xffu);
+	const unsigned todo = want & ~done[(size_t)dev];
 	int rc;
-	if ((rc = set_conv_attr<EPI_POINTS, SRC_INTER, 1> ())) return rc;
-	if ((rc = set_conv_attr<EPI_POINTS, SRC_INTER, 2> ())) return rc;
-	if ((rc = set_conv_attr<EPI_RENDER, SRC_INTER, 1> ())) return rc;
-	if ((rc = set_conv_attr<EPI_RENDER, SRC_INTER, 2> ())) return rc;
-	if ((rc = set_conv_attr<EPI_RENDER, SRC_PLANE, 1> ())) return rc;
-	if ((rc = set_conv_attr<EPI_RENDER, SRC_PLANE, 2> ())) return rc;
-	if ((rc = set_conv_attr<EPI_HILBERT, SRC_INTER, 1> ())) return rc;
-	if ((rc = set_conv_attr<EPI_HILBERT, SRC_INTER, 2> ())) return rc;
-	CK (cudaFuncSetAttribute (fir_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-	if (done.size () <= (size_t)dev) done.resize ((size_t)dev + 1, 0);
-	done[(size_t)dev] = 1;
+	if ((todo & KA_POINTS) && (rc = set_conv_attr<EPI_POINTS, SRC_INTER, 1> ())) return rc;
+	if ((todo & (KA_POINTS << 4)) && (rc = set_conv_attr<EPI_POINTS, SRC_INTER, 2> ())) return rc;
+	if ((todo & KA_RENDER_INTER) && (rc = set_conv_attr<EPI_RENDER, SRC_INTER, 1> ())) return rc;
+	if ((todo & (KA_RENDER_INTER << 4)) && (rc = set_conv_attr<EPI_RENDER, SRC_INTER, 2> ())) return rc;
+	if ((todo & KA_RENDER_PLANE) && (rc = set_conv_attr<EPI_RENDER, SRC_PLANE, 1> ())) return rc;
+	if ((todo & (KA_RENDER_PLANE << 4)) && (rc = set_conv_attr<EPI_RENDER, SRC_PLANE, 2> ())) return rc;
+	if ((todo & KA_HILBERT) && (rc = set_conv_attr<EPI_HILBERT, SRC_INTER, 1> ())) return rc;
+	if ((todo & (KA_HILBERT << 4)) && (rc = set_conv_attr<EPI_HILBERT, SRC_INTER, 2> ())) return rc;
+	if (todo & KA_FIR_STREAM) {
+		CK (cudaFuncSetAttribute (fir_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+	}
+	done[(size_t)dev] |= want;
 	return PHASEROT_OK;
 }
 
@@ -419,31 +445,7 @@ launch_conv_np (phaserot* h, const ConvParams& p)
 	}
 	const int grid = (int)std::min<long long> (total, h->n_sm);
 	ProfScope ps (h, EPI == EPI_POINTS ? 0 : EPI == EPI_HILBERT ? 6 : 3);
-	// Interleaved multichannel input: the CTAs of the channels of one stretch (block
-	// index b, b + 1, ... of equal b / nchan) form a thread-block cluster and meet
-	// once per segment, see ConvParams::pair_sync.  All CTAs of a cluster walk
-	// runs of the same length because the grid is a multiple of nchan.
-	const int csz = (SRC == SRC_INTER && h->pair_sync && p.seg_stride == 1 && p.nchan >= 2 && p.nchan <= 8 && grid % p.nchan == 0 && p.nseg * p.nchan >= grid) ? p.nchan : 1;
-	if (csz > 1) {
-		ConvParams pc = p;
-		pc.pair_sync  = csz;
-		cudaLaunchConfig_t  lc;
-		cudaLaunchAttribute at[1];
-		memset (&lc, 0, sizeof (lc));
-		lc.gridDim          = dim3 ((unsigned)grid);
-		lc.blockDim         = dim3 (kConvThreads);
-		lc.dynamicSmemBytes = kSmemBytes;
-		lc.stream           = h->stream;
-		at[0].id               = cudaLaunchAttributeClusterDimension;
-		at[0].val.clusterDim.x = (unsigned)csz;
-		at[0].val.clusterDim.y = 1;
-		at[0].val.clusterDim.z = 1;
-		lc.attrs               = at;
-		lc.numAttrs            = 1;
-		CK (cudaLaunchKernelEx (&lc, fftconv_kernel<EPI, SRC, NP>, pc));
-	} else {
-		fftconv_kernel<EPI, SRC, NP><<<grid, kConvThreads, kSmemBytes, h->stream>>> (p);
-	}
+	fftconv_kernel<EPI, SRC, NP><<<grid, kConvThreads, kSmemBytes, h->stream>>> (p);
 	CK (cudaGetLastError ());
 	++h->stats.kernel_launches;
 	return PHASEROT_OK;
@@ -512,6 +514,7 @@ init_front_pad (phaserot* h, const float* hist_frames)
 
 // bootstrap gate of the digital sweep: keep points with r^2 >= kBootBeta * (largest r^2 seen), i.e. r >= 0.8 r_max
 constexpr float kBootBeta = 0.64f;
+constexpr long long kBootCap = 64 << 10; // points per channel the bootstrap wave may put on the list
 
 inline bool OS_is_digital (const phaserot* h) { return h->OS <= 1; }
 
@@ -541,25 +544,63 @@ pick_sweep_cfg (int A)
 }
 
 int
-launch_sweep (phaserot* h, int A, int c0, int nchan, const unsigned* count)
+launch_sweep (phaserot* h, int A, int c0, int nchan, const unsigned* count, const float2* lst = nullptr, unsigned cap = 0, bool boot = false)
 {
 	const SweepCfg sc = pick_sweep_cfg (A);
 	int gx = (h->n_sm * 8) / std::max (1, sc.gy * nchan);
 	gx     = std::max (gx, 1);
 	const dim3 grid ((unsigned)gx, (unsigned)sc.gy, (unsigned)nchan);
-	const float2*       lst = (const float2*)h->d_list.p;
+	if (!lst) lst = (const float2*)h->d_list.p;
+	if (!cap) cap = (unsigned)h->list_cap;
 	const float2*       cs  = (const float2*)h->d_cs.p;
 	unsigned*           pk  = (unsigned*)h->d_peaks.p;
 	unsigned long long* ne  = d_stats (h) + 1;
 	ProfScope           ps (h, 1);
 	switch (sc.R) {
-		case 1: sweep_kernel<1><<<grid, sc.nt, 0, h->stream>>> (lst, h->list_stride, count, c0, cs, A, pk, h->pend_A, ne); break;
-		case 2: sweep_kernel<2><<<grid, sc.nt, 0, h->stream>>> (lst, h->list_stride, count, c0, cs, A, pk, h->pend_A, ne); break;
-		case 4: sweep_kernel<4><<<grid, sc.nt, 0, h->stream>>> (lst, h->list_stride, count, c0, cs, A, pk, h->pend_A, ne); break;
-		default: sweep_kernel<8><<<grid, sc.nt, 0, h->stream>>> (lst, h->list_stride, count, c0, cs, A, pk, h->pend_A, ne); break;
+		case 1: sweep_kernel<1><<<grid, sc.nt, 0, h->stream>>> (lst, h->list_stride, count, cap, boot ? 0 : 1, c0, cs, A, pk, h->pend_A, ne); break;
+		case 2: sweep_kernel<2><<<grid, sc.nt, 0, h->stream>>> (lst, h->list_stride, count, cap, boot ? 0 : 1, c0, cs, A, pk, h->pend_A, ne); break;
+		case 4: sweep_kernel<4><<<grid, sc.nt, 0, h->stream>>> (lst, h->list_stride, count, cap, boot ? 0 : 1, c0, cs, A, pk, h->pend_A, ne); break;
+		default: sweep_kernel<8><<<grid, sc.nt, 0, h->stream>>> (lst, h->list_stride, count, cap, boot ? 0 : 1, c0, cs, A, pk, h->pend_A, ne); break;
 	}
 	CK (cudaGetLastError ());
 	++h->stats.kernel_launches;
+	return PHASEROT_OK;
+}
+
+int sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frames, long long t_end, bool first_block, const float* hist,
+                int ang_start, int ang_end, int ang_stride, int chn, int fmt, bool redo);
+
+// The pending sweep is complete on the device when this returns: waits for it and,
+// if a survivor list overflowed (material where most samples survive the radius
+// filter), repeats the pass in dense mode on top of the table reached so far (a
+// running maximum only grows, and every point evaluated was a real one).  Dense
+// launches are sized to the list, so the repeat cannot overflow.
+int
+complete_pending (phaserot* h)
+{
+	if (!h->pending) {
+		return PHASEROT_OK;
+	}
+	int rc = h->h_res.ensure (64);
+	if (rc) return rc;
+	for (int attempt = 0; attempt < 2; ++attempt) {
+		unsigned long long* st = (unsigned long long*)h->h_res.p;
+		CK (cudaMemcpyAsync (st, d_stats (h), 3 * sizeof (unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+		CK (cudaStreamSynchronize (h->stream));
+		if ((unsigned)st[2] == 0) {
+			return PHASEROT_OK;
+		}
+		if (attempt == 1 || h->dense_mode) {
+			snprintf (g_last_error, sizeof (g_last_error), "survivor list overflow in dense mode");
+			return PHASEROT_E_CUDA; // cannot happen: dense launches are sized to the list
+		}
+		h->stats.points_evaluated += st[1];
+		h->dense_mode = true;
+		++h->stats.dense_repeats;
+		const phaserot::Redo r = h->redo;
+		rc = sweep_core (h, r.src, true, r.n_frames, r.t_end, r.first_block, r.hist, r.ang_start, r.ang_end, r.ang_stride, r.chn, PHASEROT_PCM_F32, true);
+		if (rc) return rc;
+	}
 	return PHASEROT_OK;
 }
 
@@ -570,12 +611,14 @@ finish_pending (phaserot* h)
 	if (!h->pending) {
 		return PHASEROT_OK;
 	}
+	int rc = complete_pending (h);
+	if (rc) return rc;
 	const int    A     = h->pend_A;
-	// [C][A] maxima | [C] raw peaks | pad to 8 bytes | 2 x u64 statistics
+	// [C][A] maxima | [C] raw peaks | pad to 8 bytes | 3 x u64 statistics
 	const size_t n_tab = (size_t)A * h->C + (size_t)h->C;
 	const size_t n_pad = n_tab + (n_tab & 1);
-	const size_t bytes = sizeof (unsigned) * n_pad + 2 * sizeof (unsigned long long);
-	int          rc    = h->h_res.ensure (bytes);
+	const size_t bytes = sizeof (unsigned) * n_pad + 3 * sizeof (unsigned long long);
+	rc                 = h->h_res.ensure (bytes);
 	if (rc) return rc;
 	unsigned* res = (unsigned*)h->h_res.p;
 	if (A > 0) {
@@ -584,7 +627,7 @@ finish_pending (phaserot* h)
 		CK (cudaMemcpyAsync (res, d_raw (h), sizeof (unsigned) * (size_t)h->C, cudaMemcpyDeviceToHost, h->stream));
 	}
 	unsigned long long* st = (unsigned long long*)(res + n_pad);
-	CK (cudaMemcpyAsync (st, d_stats (h), 2 * sizeof (unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+	CK (cudaMemcpyAsync (st, d_stats (h), 3 * sizeof (unsigned long long), cudaMemcpyDeviceToHost, h->stream));
 	CK (cudaStreamSynchronize (h->stream));
 	prof_resolve (h);
 	h->stats.d2h_bytes += bytes;
@@ -603,6 +646,10 @@ finish_pending (phaserot* h)
 		}
 	}
 	h->stats.points_evaluated += st[1];
+	// leave dense mode when the material no longer needs it (the list stayed far below the normal capacity)
+	if (h->dense_mode && !(h->cfg.flags & PHASEROT_FLAG_NO_PRUNE) && h->pend_points > 0 && (double)st[0] < 1e-3 * (double)h->pend_points) { // st[0]: points the lists held
+		h->dense_mode = false;
+	}
 	h->pending = false;
 	return PHASEROT_OK;
 }
@@ -646,14 +693,15 @@ angle_schedule (phaserot* h, int ang_start, int ang_end, int ang_stride, std::ve
  */
 int
 sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frames, long long t_end, bool first_block,
-            const float* hist, int ang_start, int ang_end, int ang_stride, int chn, int fmt = PHASEROT_PCM_F32 /* host src: PHASEROT_PCM_* */)
+            const float* hist, int ang_start, int ang_end, int ang_stride, int chn, int fmt = PHASEROT_PCM_F32 /* host src: PHASEROT_PCM_* */,
+            bool redo = false /* dense-mode repeat of the pending sweep: keep the device table */)
 {
 	// bytes per sample on the host side (and on the bus); 0 = float32, no conversion pass
 	const int pcm_bytes = fmt == PHASEROT_PCM_S16 ? 2 : fmt == PHASEROT_PCM_S32 ? 4 : fmt == PHASEROT_PCM_S24 ? 3 : 0;
 	if (chn >= h->C) {
 		return PHASEROT_E_INVAL;
 	}
-	int rc = finish_pending (h);
+	int rc = redo ? PHASEROT_OK : finish_pending (h);
 	if (rc) return rc;
 
 	std::vector<int> idx;
@@ -680,8 +728,25 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 	memcpy (h->h_cs.p, cs.data (), sizeof (float2) * cs.size ());
 	CK (cudaMemcpyAsync (h->d_cs.p, h->h_cs.p, sizeof (float2) * cs.size (), cudaMemcpyHostToDevice, h->stream));
 	h->pend_A = A; // d_raw() depends on it
-	CK (cudaMemsetAsync (h->d_peaks.p, 0, sizeof (unsigned) * ((size_t)std::max (A, 1) * h->C + (size_t)h->C), h->stream));
+	if (!redo) {
+		CK (cudaMemsetAsync (h->d_peaks.p, 0, sizeof (unsigned) * ((size_t)std::max (A, 1) * h->C + (size_t)h->C), h->stream));
+	}
 	CK (cudaMemsetAsync (h->d_small.p, 0, kSmallBytes, h->stream));
+	const bool no_prune = (h->cfg.flags & PHASEROT_FLAG_NO_PRUNE) != 0;
+	const bool dense    = h->dense_mode || no_prune; // launches sized to the survivor list
+	if (dense && !no_prune && A > 0) {
+		// grid index -> slot of the swept angle set, for sweep_window_kernel
+		rc = h->h_slot.ensure (sizeof (int) * (size_t)h->MS);
+		if (rc) return rc;
+		int* so = (int*)h->h_slot.p;
+		std::fill (so, so + h->MS, -1);
+		for (int k = 0; k < A; ++k) so[idx[(size_t)k]] = k;
+		rc = h->d_slot.ensure (sizeof (int) * (size_t)h->MS);
+		if (rc) return rc;
+		rc = h->d_sec.ensure (sizeof (float) * (size_t)kSectors * h->C);
+		if (rc) return rc;
+		CK (cudaMemcpyAsync (h->d_slot.p, so, sizeof (int) * (size_t)h->MS, cudaMemcpyHostToDevice, h->stream));
+	}
 
 	const long long m_end = (t_end + 1) / 2;
 	const long long nseg  = (m_end + h->V - 1) / h->V;
@@ -710,14 +775,36 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 	// of stereo is bootstrap + 2 launches.  The list is sized by the stream, at most
 	// 3.7 GB.  Host input keeps 8, so that little work is left when the last chunk
 	// has landed.)
-	const long long segs_first = std::max<long long> (1, ((long long)h->n_sm * 8) / nchan);
-	long long       segs_max   = !src_is_device ? segs_first : (OS_is_digital (h) ? 16 : 2) * segs_first; // true-peak: the list holds OS + 1 points per sample
-	if (getenv ("PHASEROT_SEGS_MAX")) segs_max = std::max<long long> (1, atoll (getenv ("PHASEROT_SEGS_MAX")) * h->n_sm / nchan);
-	const long long segs_cap   = std::min (segs_max, std::max<long long> (nseg, 1));
-	const int       OS       = h->OS;
-	h->list_stride           = segs_cap * h->V * 2 * (OS > 1 ? OS + 1 : 1); // true-peak: the sample and OS interpolated points
+	const int       OS         = h->OS;
+	const long long ppseg      = (long long)h->V * 2 * (OS > 1 ? OS + 1 : 1); // points a segment can put on the list (true-peak: the sample and OS interpolated points)
+	long long       segs_first = std::max<long long> (1, ((long long)h->n_sm * 8) / nchan);
+	long long       segs_max   = !src_is_device ? segs_first : (OS_is_digital (h) ? 16 : 2) * segs_first;
+	// Survivor list, sized by demand.  Normal mode: 1/32 of the points of the
+	// largest launch (pruning leaves 1e-4 .. 1e-5 of them on programme material), at
+	// least 1 M points per channel; a list that overflows flags the pass and
+	// complete_pending() repeats it in dense mode.  Dense mode (and NO_PRUNE, where
+	// every point goes on the list): at most kDenseCap points per channel, and the
+	// launches are sized to it, so nothing can overflow.
+	constexpr long long kDenseCap = 16LL << 20;
+	long long           cap;
+	if (dense) {
+		const long long fit = std::max<long long> (1, kDenseCap / ppseg);
+		segs_first          = std::min (segs_first, fit);
+		segs_max            = std::min (segs_max, fit);
+		cap                 = std::min (std::max (segs_first, segs_max), std::max<long long> (nseg, 1)) * ppseg;
+	} else {
+		const long long full = std::min (std::max (segs_first, segs_max), std::max<long long> (nseg, 1)) * ppseg;
+		cap                  = std::min (full, std::max<long long> (1LL << 20, full / 32));
+	}
+	const long long segs_cap = std::min (std::max (segs_first, segs_max), std::max<long long> (nseg, 1));
+	h->list_stride           = cap;
+	h->list_cap              = cap;
 	rc                       = h->d_list.ensure ((size_t)h->list_stride * h->C * sizeof (float2));
 	if (rc) return rc;
+	if (dense && !no_prune && A > 0) {
+		rc = h->d_wide.ensure ((size_t)h->list_stride * h->C * sizeof (float2));
+		if (rc) return rc;
+	}
 	if (OS > 1) {
 		h->tp_stride = (kTpCarry + segs_cap * h->V * 2 + 3) & ~3LL;
 		rc           = h->d_tpH.ensure (sizeof (float) * (size_t)h->tp_stride * h->C);
@@ -746,6 +833,8 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 	p.list        = (float2*)h->d_list.p;
 	p.list_stride = h->list_stride;
 	p.count       = d_count (h);
+	p.list_cap    = (unsigned)h->list_cap;
+	p.overflow    = d_overflow (h);
 	p.thr2        = d_thr2 (h);
 	p.rawpeak     = d_raw (h);
 	const int thr_mode = A == 0 ? 2 : (h->cfg.flags & PHASEROT_FLAG_NO_PRUNE) ? 0 : 1;
@@ -771,7 +860,7 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 	long long       frames_ready = 0; // frames of `inter` that are valid on the device
 	long long       seg_done     = 0;
 	const long long wave     = std::max<long long> (1, (h->n_sm + nchan - 1) / nchan); // segments per channel in one wave
-	bool            booted   = thr_mode != 1;
+	bool            booted   = thr_mode != 1 || redo; // a repeat starts from the table the first attempt reached
 	int             n_main   = 0; // contiguous launches so far
 
 	TpParams tp;
@@ -796,6 +885,8 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 		tp.list        = p.list;
 		tp.list_stride = p.list_stride;
 		tp.count       = p.count;
+		tp.list_cap    = p.list_cap;
+		tp.overflow    = p.overflow;
 		tp.thr2        = p.thr2;
 		tp.rawpeak     = p.rawpeak;
 		tp.r2max       = d_r2max (h);
@@ -807,6 +898,44 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 		CK (cudaGetLastError ());
 		++h->stats.kernel_launches;
 		return PHASEROT_OK;
+	};
+
+	// every angle over the survivors of one launch.  Normal mode: angles in lanes over the
+	// (short) list.  Dense mode: sector thresholds, then one thread per point over the few
+	// angles it can still raise (sweep_window_kernel); what that leaves goes angles-in-lanes.
+	auto sweep_survivors = [&] (const unsigned* count, unsigned cap, bool boot) -> int {
+		if (A == 0) return PHASEROT_OK;
+		if (!dense || no_prune || boot) { // (bootstrap: the running peaks are still zero, every window would be the whole grid)
+			return launch_sweep (h, A, c0, nchan, count, nullptr, cap, boot);
+		}
+		CK (cudaMemsetAsync (d_wide_count (h), 0, sizeof (unsigned) * 64, h->stream));
+		WinParams w;
+		memset (&w, 0, sizeof (w));
+		w.list         = (const float2*)h->d_list.p;
+		w.list_stride  = h->list_stride;
+		w.count        = count;
+		w.cap          = cap;
+		w.chan0        = c0;
+		w.cs           = (const float2*)h->d_cs.p;
+		w.slot_of      = (const int*)h->d_slot.p;
+		w.MS           = h->MS;
+		w.sec          = (const float*)h->d_sec.p;
+		w.peaks        = (unsigned*)h->d_peaks.p;
+		w.peaks_stride = A;
+		w.wide         = (float2*)h->d_wide.p;
+		w.wide_stride  = h->list_stride;
+		w.wide_count   = d_wide_count (h);
+		w.n_eval       = d_stats (h) + 1;
+		w.n_listed     = d_stats (h);
+		w.A            = A;
+		{
+			ProfScope ps (h, 1);
+			sector_thr_kernel<<<dim3 (kSectors, (unsigned)nchan), 64, 0, h->stream>>> ((const unsigned*)h->d_peaks.p, A, (const int*)h->d_slot.p, h->MS, c0, (float*)h->d_sec.p);
+			sweep_window_kernel<<<dim3 ((unsigned)(h->n_sm * 8), (unsigned)nchan), 256, 0, h->stream>>> (w);
+		}
+		CK (cudaGetLastError ());
+		h->stats.kernel_launches += 2;
+		return launch_sweep (h, A, c0, nchan, d_wide_count (h), (const float2*)h->d_wide.p, cap);
 	};
 
 	// one conv launch + sweep of its survivors + new filter radius
@@ -825,6 +954,8 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 			tp.seg_stride = stride;
 			tp.seg_jitter = p.seg_jitter;
 			tp.boot_beta  = boot ? kBootBeta : 0.f;
+			tp.list_cap   = boot ? (unsigned)std::min<long long> (h->list_cap, kBootCap) : (unsigned)h->list_cap;
+			tp.overflow   = boot ? d_overflow (h) + 1 : d_overflow (h);
 			{
 				ProfScope  ps (h, 6);
 				const dim3 grid ((unsigned)(n * (tp.V2 / kTpTile)), (unsigned)nchan);
@@ -841,19 +972,21 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 			p.count_reset = parity ? d_count (h) : d_count_odd (h);
 			p.boot_beta   = boot ? kBootBeta : 0.f;
 			p.seg_jitter  = boot && stride > 1;
+			// the bootstrap wave only has to raise the running peaks (any subset of its points is
+			// valid, the contiguous passes visit the segments again): what does not fit a small
+			// list is dropped without flagging the pass - on constant-envelope material every
+			// point of the wave passes the gate, and 64 K of them already pin every angle
+			p.list_cap    = boot ? (unsigned)std::min<long long> (h->list_cap, kBootCap) : (unsigned)h->list_cap;
+			p.overflow    = boot ? d_overflow (h) + 1 : d_overflow (h); // +1: a word nobody reads
 			r = launch_conv<EPI_POINTS, SRC_INTER> (h, p);
 			if (r) return r;
-			if (A > 0) {
-				r = launch_sweep (h, A, c0, nchan, p.count);
-				if (r) return r;
-			}
+			r = sweep_survivors (p.count, p.list_cap, boot);
+			if (r) return r;
 			parity ^= 1;
 			return PHASEROT_OK;
 		}
-		if (A > 0) {
-			r = launch_sweep (h, A, c0, nchan, d_count (h));
-			if (r) return r;
-		}
+		r = sweep_survivors (d_count (h), tp.list_cap, boot);
+		if (r) return r;
 		{
 			ProfScope ps (h, 5);
 			threshold_kernel<<<nchan, 256, 0, h->stream>>> ((const unsigned*)h->d_peaks.p, A, A, c0, d_thr2 (h), d_count (h), 1, thr_mode);
@@ -995,7 +1128,20 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 		rc = process_ready (true);
 		if (rc) return rc;
 	}
-	h->stats.points_total += (uint64_t)nchan * (uint64_t)(2 * (m_end - p.m_skip)) * (uint64_t)(OS > 1 ? OS + 1 : 1);
+	if (!redo) {
+		h->pend_points = (uint64_t)nchan * (uint64_t)(2 * (m_end - p.m_skip)) * (uint64_t)(OS > 1 ? OS + 1 : 1);
+		h->stats.points_total += h->pend_points;
+		// the device-resident form of this pass, should complete_pending() have to repeat it
+		h->redo.src         = p.inter;
+		h->redo.n_frames    = n_frames;
+		h->redo.t_end       = t_end;
+		h->redo.first_block = first_block;
+		h->redo.hist        = d_hist;
+		h->redo.ang_start   = ang_start;
+		h->redo.ang_end     = ang_end;
+		h->redo.ang_stride  = ang_stride;
+		h->redo.chn         = chn;
+	}
 	h->pending = true;
 	return PHASEROT_OK;
 }
@@ -1317,7 +1463,6 @@ phaserot_create (phaserot_t** out, const phaserot_cfg_t* cfg)
 	h->cfg    = *cfg;
 	h->dev    = dev;
 	h->n_sm   = prop.multiProcessorCount;
-	if (const char* e = getenv ("PHASEROT_PAIR_SYNC")) h->pair_sync = atoi (e);
 	h->C      = cfg->n_channels;
 	h->L      = L;
 	h->Lh     = L / 2;
@@ -1350,7 +1495,7 @@ phaserot_create (phaserot_t** out, const phaserot_cfg_t* cfg)
 			break;
 		}
 		h->stream = h->own_stream;
-		rc        = set_device_attrs (dev);
+		rc        = set_device_attrs (dev, plugin, h->NP, OS);
 		if (rc) break;
 		rc = h->d_small.ensure (kSmallBytes);
 		if (rc) break;
@@ -1399,10 +1544,10 @@ phaserot_destroy (phaserot_t* h)
 	if (h->own_stream) cudaStreamSynchronize (h->own_stream);
 	if (h->copy_stream) cudaStreamSynchronize (h->copy_stream);
 	for (DevBuf* b : { &h->d_G, &h->d_G1, &h->d_scratch, &h->d_tw, &h->d_g, &h->d_plane, &h->d_out, &h->d_list, &h->d_stage[0], &h->d_stage[1], &h->d_io, &h->d_inter, &h->d_hist, &h->d_small,
-	                   &h->d_cs, &h->d_peaks, &h->d_ramp, &h->d_chancs, &h->d_tpH, &h->d_ring }) {
+	                   &h->d_cs, &h->d_peaks, &h->d_ramp, &h->d_chancs, &h->d_tpH, &h->d_ring, &h->d_slot, &h->d_sec, &h->d_wide }) {
 		b->release ();
 	}
-	for (PinBuf* b : { &h->h_stage[0], &h->h_stage[1], &h->h_res, &h->h_io, &h->h_cs }) {
+	for (PinBuf* b : { &h->h_stage[0], &h->h_stage[1], &h->h_res, &h->h_io, &h->h_cs, &h->h_slot }) {
 		b->release ();
 	}
 	for (int b = 0; b < 2; ++b) {
@@ -1649,6 +1794,13 @@ phaserot_pending_table (phaserot_t* h, float** d_table, int* n_channels, int* n_
 	}
 	if (!h->pending) {
 		return PHASEROT_E_STATE;
+	}
+	{
+		// the table handed out must be final for this shard: wait for the pass and repeat it
+		// in dense mode if its survivor list overflowed (see complete_pending())
+		DevGuard  guard (h->dev);
+		const int rc = complete_pending (h);
+		if (rc) return rc;
 	}
 	*d_table    = (float*)h->d_peaks.p;
 	*n_channels = h->C;
@@ -2252,6 +2404,9 @@ phaserot_group_sweep (phaserot_group_t* g, const void* data, int format, uint64_
 		const long long t_end = lst ? (B + 1) * h->L : nf;
 		int rc = sweep_core (h, (const float*)((const char*)data + bps * (size_t)f0 * h->C), false, nf, t_end, i == 0 && B > 0,
 		                     i > 0 ? hist.data () : nullptr, ang_start, ang_end, ang_stride, chn, format);
+		if (rc == PHASEROT_OK) {
+			rc = complete_pending (h); // a shard whose survivor list overflowed is repeated in dense mode before the tables are combined
+		}
 		if (rc == PHASEROT_OK && cudaEventRecord (g->ev[(size_t)i], h->stream) != cudaSuccess) {
 			rc = PHASEROT_E_CUDA;
 		}

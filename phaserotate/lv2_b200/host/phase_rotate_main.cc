@@ -29,6 +29,8 @@
 #include <string>
 #include <vector>
 
+#include <chrono>
+
 #include <sndfile.h>
 
 #include "phaserot_cuda.h"
@@ -59,6 +61,22 @@ struct Options {
 	int          subsample   = 2;     // --subsample N: 1/N degree grid (BASELINE configs 3 and 5 use 10 and 100)
 	int          gpus        = 1;     // --gpus N: sample-range shards over N devices (0 = all)
 	bool         fixed_write = false; // --fixed-write: write loop without the reference's two quirks (cli:985, cli:973)
+};
+
+// PHASEROT_CLI_TIMING=1: wall-clock breakdown of the process on stderr (file read, CUDA
+// context + module load inside phaserot_create, analysis, render, write)
+struct StageTimer {
+	bool                                  on;
+	std::chrono::steady_clock::time_point t0, last;
+	StageTimer () : on (getenv ("PHASEROT_CLI_TIMING") != nullptr), t0 (std::chrono::steady_clock::now ()), last (t0) {}
+	void mark (const char* what)
+	{
+		if (!on) return;
+		const auto now = std::chrono::steady_clock::now ();
+		fprintf (stderr, "[timing] %-28s %8.1f ms  (at %8.1f ms)\n", what, std::chrono::duration<double, std::milli> (now - last).count (),
+		         std::chrono::duration<double, std::milli> (now - t0).count ());
+		last = now;
+	}
 };
 
 float
@@ -304,7 +322,13 @@ struct PeakTable {
 int
 main (int argc, char** argv)
 {
-	Options opt = parse_options (argc, argv);
+	StageTimer timer;
+	Options    opt = parse_options (argc, argv);
+	if (opt.gpus == 1 && !getenv ("CUDA_VISIBLE_DEVICES")) {
+		// one device is used: do not let the driver bring up every GPU of the box (most of the
+		// process start-up on an 8-GPU node); an explicit CUDA_VISIBLE_DEVICES is respected
+		setenv ("CUDA_VISIBLE_DEVICES", "0", 0);
+	}
 
 	SF_INFO nfo;
 	memset (&nfo, 0, sizeof (nfo));
@@ -382,8 +406,10 @@ main (int argc, char** argv)
 	                                                                                                                      : 0;
 	const size_t   ssize   = pcm_fmt == PHASEROT_PCM_S16 ? sizeof (short) : pcm_fmt == PHASEROT_PCM_S24 ? 3 : sizeof (float); // int and float are both 4 bytes
 	const size_t   fbytes  = std::max<size_t> (ssize * (size_t)frames * (size_t)C, 16);
+	timer.mark ("open file");
 	float*         audio   = (float*)phaserot_alloc_host (fbytes);
 	bool           pinned  = audio != nullptr;
+	timer.mark ("CUDA init + pinned buffer");
 	if (!audio) {
 		audio = (float*)malloc (fbytes);
 	}
@@ -409,6 +435,7 @@ main (int argc, char** argv)
 		got += (uint64_t)n;
 	}
 	const uint64_t F = got;
+	timer.mark ("read + decode file");
 
 	phaserot_cfg_t cfg;
 	memset (&cfg, 0, sizeof (cfg));
@@ -444,6 +471,7 @@ main (int argc, char** argv)
 	} else {
 		check (phaserot_create (&pr, &cfg), "cannot initialise the CUDA backend");
 	}
+	timer.mark ("phaserot_create (tables, kernels)");
 
 	if (find_min) {
 		const int stride = opt.stride;
@@ -462,6 +490,7 @@ main (int argc, char** argv)
 		tab.channels = C;
 		tab.t.resize ((size_t)C * kMaxSample);
 		check (phaserot_peaks (pr, tab.t.data ()), "analysis failed");
+		timer.mark ("analysis (upload + sweep)");
 		const std::vector<bool> all ((size_t)C, true);
 
 		if (opt.verbose > 1) { // gnuplot table of the coarse pass (cli:800-813)
@@ -694,11 +723,13 @@ main (int argc, char** argv)
 		}
 	}
 
+	timer.mark ("search + report + render/write");
 	if (grp) {
 		phaserot_group_destroy (grp);
 	} else {
 		phaserot_destroy (pr);
 	}
+	timer.mark ("destroy");
 	sf_close (infile);
 	if (pinned) {
 		phaserot_free_host (audio);

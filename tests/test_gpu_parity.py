@@ -55,6 +55,8 @@ SWEEP_CASES = {
     # FIR length 32768 (192 kHz files, cli:749-755): two tap partitions on the device
     "harmonic_2ch_L32768": (lambda: O.harmonic(192000, 0.9, 2), 32768),
     "short_mono_L32768": (lambda: O.pink_noise(5000, 11)[:, None], 32768),
+    # BASELINE config 5's shape: 8 interleaved channels AND the 32768-tap FIR (two tap partitions) together
+    "eight_ch_L32768": (lambda: O.harmonic(192000, 0.22, 8), 32768),
 }
 
 

@@ -54,7 +54,7 @@ def test_odd_sized_tables_read_back():
         idx = np.arange(0, 360, 8)
         assert np.max(np.abs(pk[0, idx] - po[0, idx]) / po[0, idx]) <= 1e-5
         h.reset()
-        h.sweep(x, -3, 3, 1)          # mono refine window through index 0: raw peak + odd count
+        h.sweep(x, -3, 4, 1)          # mono refine window through index 0 (the loop stops at `end`): raw peak + 6 slots + 1
         pk = h.peaks()
         for a in (-3, -2, -1, 0, 1, 2, 3):
             assert abs(pk[0, a % 360] - po[0, a % 360]) <= 1e-5 * po[0, a % 360], a
@@ -233,3 +233,104 @@ def test_cli_fixed_write(tmp_path):
     r = _cli("-f", str(L), "-a", "18.5,90.5", wav, str(tmp_path / "q.wav"))
     yq, _ = O.read_wav_f32(str(tmp_path / "q.wav"))
     assert yq.shape != y.shape or np.max(np.abs(yq - y)) > 1e-3
+
+
+def _tones(seconds, parts, sr=48000):
+    t = np.arange(int(seconds * sr), dtype=np.float64) / sr
+    x = np.zeros((t.size, 2), np.float32)
+    for c in range(2):
+        acc = np.zeros(t.size)
+        for amp, f, ph in parts:
+            acc += amp * np.sin(2 * np.pi * f * t + ph[c])
+        x[:, c] = acc
+    return x
+
+
+def test_dense_mode_constant_envelope_equals_brute_force():
+    """A pure sine: every sample lies on the hull of the (x_d, H) point set, the radius filter keeps
+    them all and the survivor list (sized for programme material) overflows.  The pass is repeated in
+    dense mode (sector thresholds + per-point angle windows) and the table still equals brute force bit
+    for bit; the handle stays dense for the same material and returns to normal mode on programme."""
+    import torch
+    x = _tones(40.0, [(0.5, 440.0, [0.0, 1.0])])
+    xd = torch.from_numpy(x).cuda()
+    with capi.Phaserot(n_channels=2, blksiz=8192, subsample=10, flags=capi.FLAG_NO_PRUNE) as hb:
+        hb.sweep_device(xd.data_ptr(), x.shape[0])
+        brute = hb.peaks()
+    with capi.Phaserot(n_channels=2, blksiz=8192, subsample=10) as h:
+        h.sweep_device(xd.data_ptr(), x.shape[0])
+        got = h.peaks()
+        st = h.stats()
+        assert st["dense_repeats"] == 1
+        assert np.array_equal(got, brute)
+        assert st["points_evaluated"] < 0.1 * st["points_total"]      # windows, not every angle
+        h.reset()
+        h.sweep_device(xd.data_ptr(), x.shape[0])                     # sticky: no second repeat
+        assert np.array_equal(h.peaks(), brute)
+        assert h.stats()["dense_repeats"] == 1
+        # host source in dense mode, sharded, and the reference grid
+        h.reset()
+        al = h.shard_align()
+        cut = al * ((x.shape[0] // 2) // al)
+        h.sweep_shard(np.ascontiguousarray(x[:cut]), cut, None, True, False)
+        a = h.peaks()
+        h.reset()
+        h.sweep_shard(np.ascontiguousarray(x[cut:]), x.shape[0] - cut, x[cut - 8192:cut], False, True)
+        assert np.array_equal(np.maximum(a, h.peaks()), brute)
+        # programme material: the handle leaves dense mode again
+        prog = O.programme(48000, 40.0, 2)
+        h.reset()
+        h.sweep(prog)
+        p1 = h.peaks()
+        h.reset()
+        h.sweep(prog)
+        assert np.array_equal(h.peaks(), p1)
+        assert h.stats()["dense_repeats"] == 1
+    with capi.Phaserot(n_channels=2, blksiz=8192, subsample=10, flags=capi.FLAG_NO_PRUNE) as hb:
+        hb.sweep(prog)
+        assert np.array_equal(p1, hb.peaks())
+    # reference grid, against the oracle (3 s)
+    s3 = x[:144000]
+    po = O.oracle_analyze(s3, 8192)
+    with capi.Phaserot(n_channels=2, blksiz=8192) as h:
+        h.sweep(s3)
+        assert np.max(np.abs(h.peaks() - po) / po) <= 1e-5
+
+
+def test_dense_mode_two_tone_and_true_peak():
+    """Config-1 material long enough to overflow the list (few-tone: a third of the samples survive the
+    radius filter until the table has converged), digital and 4x true-peak: dense-mode tables equal
+    brute force bit for bit."""
+    import torch
+    x = _tones(60.0, [(0.5, 110.0, [0.0, 1.0]), (0.25, 1760.3, [0.0, 0.0])])
+    xd = torch.from_numpy(x).cuda()
+    for os_ in (0, 4):
+        with capi.Phaserot(n_channels=2, blksiz=8192, subsample=10, flags=capi.FLAG_NO_PRUNE, oversample=os_) as hb:
+            hb.sweep_device(xd.data_ptr(), x.shape[0])
+            brute = hb.peaks()
+        with capi.Phaserot(n_channels=2, blksiz=8192, subsample=10, oversample=os_) as h:
+            h.sweep_device(xd.data_ptr(), x.shape[0])
+            assert np.array_equal(h.peaks(), brute), os_
+
+
+def test_batch_render_per_track_angles():
+    """BASELINE config 4 in small: a batch of stereo tracks, each rendered at its own per-channel angles
+    (theta_i = (i * 37 mod 360) half degrees and its mirror) through one handle that is reset between tracks -
+    host buffers and device buffers - against the oracle's render of every track."""
+    import torch
+    L = 8192
+    tracks = [O.programme(48000, 0.7 + 0.1 * i, 2, seed=1000 + i) for i in range(5)]
+    with capi.Phaserot(n_channels=2, blksiz=L) as h:
+        for i, x in enumerate(tracks):
+            ang = [(i * 37) % 360, (360 - i * 37) % 360]
+            want = O.oracle_apply(x, L, ang, 1)
+            h.reset()
+            y = h.render(x, ang, 1)
+            assert y.shape == want.shape
+            assert np.max(np.abs(y - want)) <= 1e-5 * float(np.abs(want).max()), i
+            xd = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+            yd = torch.empty((want.shape[0], 2), device="cuda", dtype=torch.float32)
+            h.reset()
+            h.render_device(xd.data_ptr(), x.shape[0], ang, 1, yd.data_ptr())
+            torch.cuda.synchronize()
+            assert np.array_equal(yd.cpu().numpy(), y), i
