@@ -484,10 +484,10 @@ class SweepBench:
 
     def combine(self, handle):
         """NCCL max all-reduce, in place, on the handle's device-resident table of the pending sweep
-        (per-angle maxima + raw peaks; phaserot_pending_table): no host round trip."""
+        (per-angle maxima + raw peaks + the library's list-overflow flag; phaserot_pending_table): no host round trip."""
         torch = self.torch
         ptr, nc, na = handle.pending_table()
-        n = nc * na + nc
+        n = nc * na + nc + 1
         t = self.tables.get((ptr, n))
         if t is None:
             class _Dev:
@@ -495,13 +495,24 @@ class SweepBench:
             t = self.tables[(ptr, n)] = torch.as_tensor(_Dev(), device=self.dev)
         self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
 
+    def combined_peaks(self, handle):
+        """all-reduce + read-back; E_AGAIN (some rank's survivor list overflowed: every rank has re-enqueued its shard in
+        dense mode, see phaserot_pending_table) means: reduce the new pending tables once more."""
+        while True:
+            self.combine(handle)
+            try:
+                return handle.peaks()  # sync + D2H of the combined table
+            except self.capi.PhaserotError as ex:
+                if ex.code != self.capi.E_AGAIN:
+                    raise
+
     def step_device(self):
         h = self.h
         h.reset()
         h.sweep_shard_device(self.x.data_ptr(), self.frames, self.hist_ptr, self.first, self.last)
         if self.world > 1:
-            self.combine(h)
-        return h.peaks()  # sync + D2H of the (combined) table
+            return self.combined_peaks(h)
+        return h.peaks()  # sync + D2H of the table
 
     def barrier(self):
         if self.world > 1:
@@ -526,9 +537,23 @@ class SweepBench:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         return float(t.item())
 
+    def check_ranks_agree(self):
+        """Every rank must hold the same combined table (max and min over the ranks coincide): catches a collective
+        that was not ordered behind the sweep, or ranks that disagreed about a repeat."""
+        if self.world == 1:
+            return
+        torch = self.torch
+        t = torch.from_numpy(self.step_device()).to(self.dev)
+        hi, lo = t.clone(), t.clone()
+        self.dist.all_reduce(hi, op=self.dist.ReduceOp.MAX)
+        self.dist.all_reduce(lo, op=self.dist.ReduceOp.MIN)
+        if not torch.equal(hi, lo) or not bool((t[:, 1:] > 0).all()):
+            raise RuntimeError("ranks disagree about the combined peak table")
+
     def run_device(self, steps, warmup, sampler=None, wall=False):
         for _ in range(max(warmup, 3)):
             self.step_device()
+        self.check_ranks_agree()
         self.h.reset_stats()
         if sampler is not None:
             sampler.start()
@@ -555,7 +580,8 @@ class SweepBench:
                 he.sweep((xh.data_ptr(), self.frames))
             else:
                 he.sweep_shard(xh.data_ptr(), self.frames, self.hist_ptr, self.first, self.last)
-                self.combine(he)
+                self.combined_peaks(he)
+                return
             he.peaks()
 
         for _ in range(2):
@@ -569,6 +595,20 @@ class SweepBench:
         if self.world > 1:
             self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
         he.close()
+        # the ceiling of this leg: the same pinned buffer copied to the device and nothing else, all ranks at once
+        # (one PCIe link per GPU, but the ranks share the host's memory system)
+        for _ in range(2):
+            self.x.copy_(xh, non_blocking=True)
+        self.barrier()
+        w0 = time.perf_counter()
+        for _ in range(steps):
+            self.x.copy_(xh, non_blocking=True)
+            torch.cuda.synchronize()
+        self.barrier()
+        tb = torch.tensor([time.perf_counter() - w0], device=self.dev, dtype=torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(tb, op=self.dist.ReduceOp.MAX)
+        self.bare_h2d_ms = 1e3 * float(tb.item()) / steps
         del xh
         return float(t.item())
 
@@ -640,9 +680,15 @@ def gpu_main(args):
         raise RuntimeError("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # Everything runs on ONE explicit stream: the handles are told to use it (phaserot_set_stream) and torch orders
+    # its NCCL collectives against the current stream.  The legacy default stream has handle 0, which
+    # phaserot_set_stream() reads as "back to the handle's private stream" - the all-reduce would then not be
+    # ordered behind the sweep at all.
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))
     numa = bind_to_gpu_numa_node(torch, local)  # before any page-locked buffer exists: host memory local to the GPU's socket
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=90))  # a mismatched collective must not hold the box for ten minutes
 
     wl = dict(WORKLOADS["config5" if args.config == "5" else "headline"])
     wl["S"] = args.subsample if args.config != "5" else wl["S"]
@@ -693,6 +739,7 @@ def gpu_main(args):
             k2 = ss.kernel_times()
             extra["strong"] = {"value": float(jf) * wl["C"] * A * args.steps / t / 1e9, "ms_per_step": 1e3 * t / args.steps,
                                "e2e_value": float(jf) * wl["C"] * A * e2e_steps / te / 1e9, "e2e_ms_per_step": 1e3 * te / e2e_steps,
+                               "bare_h2d_ms_per_step": ss.bare_h2d_ms,
                                "kernels_ms_rank0": {k: round(v["ms"], 4) for k, v in k2.items() if v["launches"]}}
             ss.close()
         extra["strong"].update({"unit": "Gsample-angles/s", "scaling": "strong",
@@ -755,6 +802,7 @@ def gpu_main(args):
                     "host_numa_binding": ("rank bound to %d GPU-local CPUs" % len(numa)) if numa else "none",
                     "d2h_bytes_per_step": int((wl["C"] * A + wl["C"]) * 4 * world), "steps": e2e_steps,
                     "ms_per_step": 1e3 * t_e2e / e2e_steps,
+                    "bare_h2d_ms_per_step": sb.bare_h2d_ms, "vs_bare_h2d": 1e3 * t_e2e / e2e_steps / sb.bare_h2d_ms,
                     "path": "phaserot_sweep (N = 1) / phaserot_sweep_shard (N > 1): pinned host buffer, chunked upload overlapped with the sweep"},
             "gpu_launches": int(launches.item()),
             "roofline": roof,

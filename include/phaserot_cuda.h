@@ -43,7 +43,8 @@ enum {
 	PHASEROT_E_CUDA        = -3, /* a CUDA call failed; see phaserot_last_error() */
 	PHASEROT_E_NOMEM       = -4, /* host or device allocation failed */
 	PHASEROT_E_UNSUPPORTED = -5, /* valid for the reference but not implemented on the device path yet */
-	PHASEROT_E_STATE       = -6  /* call not valid for this handle's mode */
+	PHASEROT_E_STATE       = -6, /* call not valid for this handle's mode */
+	PHASEROT_E_AGAIN       = -7  /* sharded sweep only, see phaserot_pending_table(): combine the pending tables once more */
 };
 
 enum {
@@ -109,8 +110,11 @@ PHASEROT_API void phaserot_destroy (phaserot_t* h);
 PHASEROT_API int phaserot_reset (phaserot_t* h);
 
 /* Run all work of this handle on a caller-owned CUDA stream (cudaStream_t),
- * e.g. the stream a framework times with its own events.  NULL restores the
- * handle's private stream. */
+ * e.g. the stream a framework times with its own events and orders its
+ * collectives against.  NULL restores the handle's private (non-blocking)
+ * stream - so the legacy default stream, whose handle IS 0, cannot be selected
+ * by passing it: use a created stream, or the special handles cudaStreamLegacy /
+ * cudaStreamPerThread. */
 PHASEROT_API int phaserot_set_stream (phaserot_t* h, void* cuda_stream);
 
 /* ---- CLI analysis: min-peak sweep -------------------------------------- */
@@ -224,15 +228,23 @@ PHASEROT_API int  phaserot_group_reset (phaserot_group_t* g);
 
 /* Device-resident result of the sweep that is still pending (enqueued, not read
  * back yet), for combining shards without a host round trip: *d_table points at
- * n_channels * n_angles + n_channels floats owned by the handle - the running
- * per-angle maxima [channel][angle slot] followed by the raw input peak of every
- * channel (the value of grid index 0, cli:413-414).  All values are >= 0, so an
- * element-wise max over the shards' buffers (NCCL all-reduce, ncclMax, in place,
- * enqueued after the sweep on the handle's stream) is the result of the whole
- * stream; the next phaserot_peak()/phaserot_peaks()/phaserot_sync() then reads
- * the combined table back on every rank.  Replaces the merge of the per-thread
- * `_peak` rows in PhaseRotate::analyze (cli:431-444) across devices.
- * PHASEROT_E_STATE when no sweep is pending. */
+ * n_channels * n_angles + n_channels + 1 floats owned by the handle - the running
+ * per-angle maxima [channel][angle slot], the raw input peak of every channel
+ * (the value of grid index 0, cli:413-414), and one word of the library's own:
+ * non-zero when this shard's survivor list overflowed (see phaserot_sweep).  All
+ * values are >= 0, so an element-wise max over the shards' WHOLE buffers (NCCL
+ * all-reduce, ncclMax, in place, enqueued after the sweep on the handle's stream;
+ * nothing is synchronised here) is the result of the whole stream; the next
+ * phaserot_peaks()/phaserot_sync() then reads the combined table back on every
+ * rank.  Because the flag is part of the reduced buffer every rank learns in the
+ * same step that some shard was incomplete: phaserot_peaks()/phaserot_sync()
+ * then return PHASEROT_E_AGAIN on EVERY rank after re-enqueueing the rank's
+ * shard in dense mode on top of the combined table - the caller repeats
+ *     phaserot_pending_table() -> all-reduce -> phaserot_peaks()
+ * once (dense launches cannot overflow).  Programme material never takes that
+ * path.  Replaces the merge of the per-thread `_peak` rows in
+ * PhaseRotate::analyze (cli:431-444) across devices.  PHASEROT_E_STATE when no
+ * sweep is pending. */
 PHASEROT_API int phaserot_pending_table (phaserot_t* h, float** d_table, int* n_channels, int* n_angles);
 
 /* Block-streaming drop-in for PhaseRotate::analyze (cli:431-444): feed one

@@ -20,7 +20,7 @@
  * Pinning: the reference ships no golden vectors or tests.  This restatement is
  * pinned against outputs of the reference's own sources, compiled unmodified
  * against stand-in fftw3/sndfile/LV2 headers (oracle/Makefile -> oracle/_ref/),
- * by tests/test_oracle_vs_ref.py, and against fixtures generated from those
+ * by tests/test_oracle.py, and against fixtures generated from those
  * binaries (tests/golden/, script tests/golden/make_golden.py).
  */
 #include <math.h>

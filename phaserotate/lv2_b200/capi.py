@@ -12,7 +12,7 @@ import numpy as np
 from . import build as _build
 
 OK = 0
-E_INVAL, E_NO_DEVICE, E_CUDA, E_NOMEM, E_UNSUPPORTED, E_STATE = -1, -2, -3, -4, -5, -6
+E_INVAL, E_NO_DEVICE, E_CUDA, E_NOMEM, E_UNSUPPORTED, E_STATE, E_AGAIN = -1, -2, -3, -4, -5, -6, -7
 MODE_CLI, MODE_PLUGIN = 0, 1
 FLAG_NO_FIRST_BLOCK_QUIRK = 1
 FLAG_NO_PRUNE = 2
@@ -244,7 +244,8 @@ class Phaserot:
                                                        ang_start, ang_end, stride, chn), "phaserot_sweep_shard_device")
 
     def pending_table(self):
-        """(device pointer, n_channels, n_angles) of the pending sweep's table: n_channels * n_angles + n_channels floats."""
+        """(device pointer, n_channels, n_angles) of the pending sweep's table: n_channels * n_angles + n_channels + 1 floats
+        (maxima, raw peaks, the library's overflow flag: reduce ALL of them; peaks() raising E_AGAIN means: combine once more)."""
         p, nc, na = C.POINTER(C.c_float)(), C.c_int(), C.c_int()
         self._ck(self._lib.phaserot_pending_table(self._h, C.byref(p), C.byref(nc), C.byref(na)), "phaserot_pending_table")
         return C.cast(p, C.c_void_p).value, nc.value, na.value

@@ -208,7 +208,7 @@ __device__ __forceinline__ void append_points (const ListDst& d, bool k0, float2
 		unsigned  base = 0;
 		if (lane == 0) {
 			base = atomicAdd (d.cnt, (unsigned)(n0 + __popc (b1)));
-			if (base + (unsigned)(n0 + __popc (b1)) > d.cap) *d.ovf = 1u; // rare: the host repeats the pass (dense mode)
+			if (base + (unsigned)(n0 + __popc (b1)) > d.cap) *d.ovf = 0x3f800000u; // rare: the pass is repeated in dense mode (bits of 1.0f: the flag is a table element)
 		}
 		base = __shfl_sync (0xffffffffu, base, 0);
 		const unsigned i0 = base + __popc (b0 & lt), i1 = base + n0 + __popc (b1 & lt);
@@ -233,7 +233,7 @@ __device__ __forceinline__ void append_points4 (const ListDst& d, const bool (&k
 	unsigned base = 0;
 	if (lane == 0) {
 		base = atomicAdd (d.cnt, (unsigned)n);
-		if (base + (unsigned)n > d.cap) *d.ovf = 1u;
+		if (base + (unsigned)n > d.cap) *d.ovf = 0x3f800000u;
 	}
 	base = __shfl_sync (0xffffffffu, base, 0);
 #pragma unroll
@@ -903,8 +903,8 @@ __global__ void threshold_kernel (const unsigned* __restrict__ peaks, int peaks_
 // handful of angles instead of all of them.  Points that still need more than
 // kWideEvals evaluations go to a second list for sweep_kernel (angles in lanes).
 // All margins err towards evaluating: 4e-6 relative on T / r (the fp32
-// evaluation of y and r is good to ~3e-7), 2e-5 rad + one grid step on every
-// angular bound (atan2f / acosf / the LUT's own rounding are below 2e-6 rad).
+// evaluation of y and r is good to ~3e-7), 6e-5 rad + one grid step on every
+// angular bound (the fast atan2 is good to 2e-5 rad, the LUT's own rounding to 2e-6 rad).
 // ---------------------------------------------------------------------------
 constexpr int kSectors   = 60;  // divides 180 * S for every S
 constexpr int kWideEvals = 768;
@@ -943,14 +943,35 @@ struct WinParams {
 	unsigned*       wide_count; // [C]
 	unsigned long long* n_eval; // statistics: point-angle evaluations / A
 	unsigned long long* n_listed; // statistics: points on the lists of this sweep
+	int             slot_base; // >= 0: the swept set is a run of consecutive grid indices, slot = grid index - slot_base (no table)
+	int             smem_tables; // 1: (ca, sa) and a snapshot of the running peaks sit in shared memory (A * 12 bytes)
 	int             A;
 };
 
 // acos (q) <= sqrt (2 u) (1 + 0.12 u), u = 1 - q in [0, 1]  (series sqrt(2u)(1 + u/12 + 3u^2/160 + ...); 1.584 >= pi/2 at u = 1)
 __device__ __forceinline__ float acos_upper (float q)
 {
-	const float u = fmaxf (1.f - q, 0.f);
-	return sqrtf (2.f * u) * fmaf (0.12f, u, 1.f) * 1.000001f;
+	const float u = fmaxf (1.f - q, 1e-30f);
+	return (2.f * u) * rsqrtf (2.f * u) * fmaf (0.12f, u, 1.00001f); // sqrt via MUFU.RSQ (2 ulp), rounded up by the factor
+}
+
+// atan2 to 2e-5 rad (polynomial of Abramowitz & Stegun 4.4.49 on [0, 1], 1e-5; approximate division): the window
+// bounds carry 4e-5 rad of slack for it
+__device__ __forceinline__ float atan2_fast (float y, float x)
+{
+	const float ax = fabsf (x), ay = fabsf (y);
+	const float mx = fmaxf (ax, ay), mn = fminf (ax, ay);
+	const float z  = __fdividef (mn, fmaxf (mx, 1e-30f));
+	const float z2 = z * z;
+	float       p  = fmaf (-0.0117212f, z2, 0.05265332f);
+	p              = fmaf (p, z2, -0.11643287f);
+	p              = fmaf (p, z2, 0.19354346f);
+	p              = fmaf (p, z2, -0.33262347f);
+	p              = fmaf (p, z2, 0.99997726f);
+	float a        = z * p;
+	if (ay > ax) a = 1.57079632679f - a;
+	if (x < 0.f) a = 3.14159265359f - a;
+	return y < 0.f ? -a : a;
 }
 
 __global__ void __launch_bounds__ (256) sweep_window_kernel (const WinParams p)
@@ -962,6 +983,18 @@ __global__ void __launch_bounds__ (256) sweep_window_kernel (const WinParams p)
 	const float    inv_G = 1.f / (float)G;
 	const float*   sec = p.sec + c * kSectors;
 	unsigned*      pk  = p.peaks + (long long)c * p.peaks_stride;
+	// The per-angle tables are hit at a different entry by every lane (neighbouring list entries are
+	// neighbouring samples, whose directions differ by the signal's phase advance): from L1 that is one
+	// 128-byte line per lane and load; from shared memory it is a bank conflict of degree ~3.
+	extern __shared__ __align__ (16) unsigned char win_sm[];
+	float2*   s_cs = reinterpret_cast<float2*> (win_sm);
+	unsigned* s_pk = reinterpret_cast<unsigned*> (s_cs + p.A);
+	if (p.smem_tables) {
+		for (int k = threadIdx.x; k < p.A; k += blockDim.x) {
+			s_cs[k] = p.cs[k];
+			s_pk[k] = pk[k];
+		}
+	}
 	// global threshold = the smallest sector threshold (every running peak is at least that)
 	__shared__ float tg_s;
 	if (threadIdx.x < 32) {
@@ -980,21 +1013,21 @@ __global__ void __launch_bounds__ (256) sweep_window_kernel (const WinParams p)
 		if (!(r2 > 0.f)) continue;
 		const float ri = rsqrtf (r2) * (1.f - 1e-6f); // a lower bound of 1 / r: thresholds over r come out low, windows wide
 		// fractional grid index of the direction of the point: alpha = phi (mod pi)  <=>  j = -phi / step (mod MS)
-		const float jc = -atan2f (q.y, q.x) * inv_step;
+		const float jc = -atan2_fast (q.y, q.x) * inv_step;
 		// reach of the global threshold in grid steps
-		const float rg = (acos_upper (tg * ri) + 2e-5f) * inv_step + 1.f;
+		const float rg = (acos_upper (tg * ri) + 6e-5f) * inv_step + 1.f;
 		bool        wide = !(2.f * rg + 2.f < (float)p.MS); // (nearly) the whole grid
 		int         done = 0;
 		if (!wide) {
-			const int s_lo = (int)floorf ((jc - rg) * inv_G), s_hi = (int)floorf ((jc + rg) * inv_G);
-			for (int su = s_lo; su <= s_hi && !wide; ++su) {
-				int sm = su % kSectors;
-				if (sm < 0) sm += kSectors;
+			const int s_lo = __float2int_rd ((jc - rg) * inv_G), s_hi = __float2int_rd ((jc + rg) * inv_G);
+			int       sm   = s_lo % kSectors;
+			if (sm < 0) sm += kSectors;
+			for (int su = s_lo; su <= s_hi && !wide; ++su, sm = sm + 1 == kSectors ? 0 : sm + 1) {
 				const float qs = sec[sm] * (1.f - 4e-6f) * ri; // T_s / r
 				if (!(qs <= 1.f)) continue;                    // nothing swept in the sector, or its threshold is above r
 				// angular half width within which the point can still reach the sector's threshold
-				const float rs = (acos_upper (qs) + 2e-5f) * inv_step + 1.f;
-				const int   j0 = max (su * G, (int)ceilf (jc - rs)), j1 = min (su * G + G - 1, (int)floorf (jc + rs));
+				const float rs = (acos_upper (qs) + 6e-5f) * inv_step + 1.f;
+				const int   j0 = max (su * G, __float2int_ru (jc - rs)), j1 = min (su * G + G - 1, __float2int_rd (jc + rs));
 				if (j1 < j0) continue;                         // the sector lies outside that window
 				done += j1 - j0 + 1;
 				if (done > kWideEvals) {
@@ -1004,12 +1037,21 @@ __global__ void __launch_bounds__ (256) sweep_window_kernel (const WinParams p)
 				int jj = j0 % p.MS;
 				if (jj < 0) jj += p.MS;
 				for (int j = j0; j <= j1; ++j) {
-					const int k = p.slot_of[jj];
+					int k = jj - p.slot_base;
+					if (p.slot_base < 0) k = p.slot_of[jj];
+					else if (k >= p.A) k = -1;
 					if (++jj == p.MS) jj = 0;
 					if (k < 0) continue;
-					const float2 w = p.cs[k];
-					const float  y = fabsf (fmaf (w.x, q.x, w.y * q.y)); // sweep_kernel's expression
-					if (__float_as_uint (y) > pk[k]) atomicMax (pk + k, __float_as_uint (y));
+					const float2   w  = p.smem_tables ? s_cs[k] : p.cs[k];
+					const unsigned yb = __float_as_uint (fabsf (fmaf (w.x, q.x, w.y * q.y))); // sweep_kernel's expression
+					if (p.smem_tables) {
+						if (yb > s_pk[k]) { // the snapshot only lags behind the table: a stale value costs an atomic, never a maximum
+							atomicMax (s_pk + k, yb);
+							atomicMax (pk + k, yb);
+						}
+					} else if (yb > pk[k]) {
+						atomicMax (pk + k, yb);
+					}
 				}
 			}
 			evals += (unsigned long long)done;
@@ -1231,7 +1273,7 @@ __device__ __forceinline__ void tp_append (float2* lst, unsigned* cnt, unsigned 
 		unsigned base = 0;
 		if (lane == 31) {
 			base = atomicAdd (cnt, (unsigned)inc);
-			if (base + (unsigned)inc > cap) *ovf = 1u;
+			if (base + (unsigned)inc > cap) *ovf = 0x3f800000u;
 		}
 		base          = __shfl_sync (0xffffffffu, base, 31);
 		unsigned pos  = base + (unsigned)(inc - nk);

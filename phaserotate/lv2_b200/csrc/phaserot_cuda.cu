@@ -216,6 +216,9 @@ struct phaserot {
 		int          ang_start = 0, ang_end = 0, ang_stride = 1, chn = -1;
 	} redo;
 	uint64_t pend_points = 0; // points examined by the pending sweep (statistics; dense-mode exit test)
+	int      pend_again   = 0;     // PHASEROT_E_AGAIN returned for the pending sweep so far
+	bool     pend_exposed = false; // the pending table was handed out (phaserot_pending_table): the caller combines shards
+	bool     pend_redone = false; // the pending sweep was repeated in dense mode (its list counts start from a raised table)
 	DevBuf d_tpH; // true-peak staging of the Hilbert branch: [C][tp_stride] floats
 	long long tp_stride = 0;
 	int       OS        = 1; // 1 = digital peak, 2 / 4 = oversampled true-peak
@@ -280,7 +283,6 @@ struct DevGuard {
 // d_small: count[64] | thr2[64] | raw[64] | ramp_len[64] | stats[2 x u64] | count of odd launches[64] | r2max[64]
 // ... | stats[3 x u64: points listed in dense mode, evaluated points, list overflow flag] | count of odd launches[64] | r2max[64] | wide list count[64]
 constexpr size_t kSmallBytes = 7 * 64 * sizeof (int) + 3 * sizeof (unsigned long long);
-static_assert (sizeof (unsigned long long) == 2 * sizeof (unsigned), "d_overflow () + 1 is the unread upper half of the flag word");
 struct ProfScope {
 	phaserot* h;
 	size_t    slot = (size_t)-1;
@@ -328,7 +330,11 @@ float*              d_thr2 (phaserot* h) { return (float*)h->d_small.p + 64; }
 unsigned*           d_raw (phaserot* h) { return (unsigned*)h->d_peaks.p + (size_t)std::max (h->pend_A, 1) * h->C; }
 int*                d_ramplen (phaserot* h) { return (int*)h->d_small.p + 192; }
 unsigned long long* d_stats (phaserot* h) { return (unsigned long long*)((char*)h->d_small.p + 4 * 64 * sizeof (int)); }
-unsigned*           d_overflow (phaserot* h) { return (unsigned*)(d_stats (h) + 2); }
+// List-overflow flag of the pending sweep: the word behind the raw peaks, i.e. the LAST element of the
+// device table (bits of 1.0f when set).  It travels with the table through an external max all-reduce, so
+// every rank of a sharded sweep learns that some shard is incomplete without a second collective.
+unsigned*           d_overflow (phaserot* h) { return d_raw (h) + h->C; }
+unsigned*           d_overflow_ignored (phaserot* h) { return (unsigned*)(d_stats (h) + 2); } // bootstrap launches: nobody reads it
 unsigned*           d_count_odd (phaserot* h) { return (unsigned*)((char*)h->d_small.p + 4 * 64 * sizeof (int) + 3 * sizeof (unsigned long long)); }
 unsigned*           d_r2max (phaserot* h) { return d_count_odd (h) + 64; }
 unsigned*           d_wide_count (phaserot* h) { return d_r2max (h) + 64; }
@@ -514,7 +520,11 @@ init_front_pad (phaserot* h, const float* hist_frames)
 
 // bootstrap gate of the digital sweep: keep points with r^2 >= kBootBeta * (largest r^2 seen), i.e. r >= 0.8 r_max
 constexpr float kBootBeta = 0.64f;
-constexpr long long kBootCap = 64 << 10; // points per channel the bootstrap wave may put on the list
+// Points per channel the bootstrap wave may put on the list.  It must hold what the gate passes on ordinary
+// material (the list fills in arrival order: a list that is too small keeps the early, weak points - the gate is
+// still low then - and the main passes start from poor peaks); on constant-envelope material the gate passes
+// every point of the wave and this cap bounds the brute-force sweep of the bootstrap to ~0.2 ms.
+constexpr long long kBootCap = 1 << 20;
 
 inline bool OS_is_digital (const phaserot* h) { return h->OS <= 1; }
 
@@ -585,8 +595,13 @@ complete_pending (phaserot* h)
 	if (rc) return rc;
 	for (int attempt = 0; attempt < 2; ++attempt) {
 		unsigned long long* st = (unsigned long long*)h->h_res.p;
-		CK (cudaMemcpyAsync (st, d_stats (h), 3 * sizeof (unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+		CK (cudaMemcpyAsync (st, d_stats (h), 2 * sizeof (unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+		CK (cudaMemcpyAsync (st + 2, d_overflow (h), sizeof (unsigned), cudaMemcpyDeviceToHost, h->stream));
 		CK (cudaStreamSynchronize (h->stream));
+		if (getenv ("PHASEROT_DEBUG")) {
+			fprintf (stderr, "[phaserot] complete (attempt %d): listed %llu evaluated %llu overflow %llx dense %d cap %lld\n", attempt, st[0], st[1], st[2],
+			         (int)h->dense_mode, h->list_cap);
+		}
 		if ((unsigned)st[2] == 0) {
 			return PHASEROT_OK;
 		}
@@ -595,7 +610,8 @@ complete_pending (phaserot* h)
 			return PHASEROT_E_CUDA; // cannot happen: dense launches are sized to the list
 		}
 		h->stats.points_evaluated += st[1];
-		h->dense_mode = true;
+		h->dense_mode  = true;
+		h->pend_redone = true;
 		++h->stats.dense_repeats;
 		const phaserot::Redo r = h->redo;
 		rc = sweep_core (h, r.src, true, r.n_frames, r.t_end, r.first_block, r.hist, r.ang_start, r.ang_end, r.ang_stride, r.chn, PHASEROT_PCM_F32, true);
@@ -611,26 +627,54 @@ finish_pending (phaserot* h)
 	if (!h->pending) {
 		return PHASEROT_OK;
 	}
-	int rc = complete_pending (h);
-	if (rc) return rc;
+	int rc = PHASEROT_OK;
+	if (!h->pend_exposed) {
+		rc = complete_pending (h); // repeats the pass in dense mode if a list overflowed
+		if (rc) return rc;
+	}
 	const int    A     = h->pend_A;
-	// [C][A] maxima | [C] raw peaks | pad to 8 bytes | 3 x u64 statistics
-	const size_t n_tab = (size_t)A * h->C + (size_t)h->C;
+	// [C][A] maxima | [C] raw peaks | overflow flag | pad to 8 bytes | 2 x u64 statistics
+	const size_t n_tab = (size_t)A * h->C + (size_t)h->C + 1;
 	const size_t n_pad = n_tab + (n_tab & 1);
-	const size_t bytes = sizeof (unsigned) * n_pad + 3 * sizeof (unsigned long long);
+	const size_t bytes = sizeof (unsigned) * n_pad + 2 * sizeof (unsigned long long);
 	rc                 = h->h_res.ensure (bytes);
 	if (rc) return rc;
 	unsigned* res = (unsigned*)h->h_res.p;
 	if (A > 0) {
-		CK (cudaMemcpyAsync (res, h->d_peaks.p, sizeof (unsigned) * ((size_t)A * h->C + (size_t)h->C), cudaMemcpyDeviceToHost, h->stream));
+		CK (cudaMemcpyAsync (res, h->d_peaks.p, sizeof (unsigned) * n_tab, cudaMemcpyDeviceToHost, h->stream));
 	} else {
-		CK (cudaMemcpyAsync (res, d_raw (h), sizeof (unsigned) * (size_t)h->C, cudaMemcpyDeviceToHost, h->stream));
+		CK (cudaMemcpyAsync (res, d_raw (h), sizeof (unsigned) * ((size_t)h->C + 1), cudaMemcpyDeviceToHost, h->stream));
 	}
 	unsigned long long* st = (unsigned long long*)(res + n_pad);
-	CK (cudaMemcpyAsync (st, d_stats (h), 3 * sizeof (unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+	CK (cudaMemcpyAsync (st, d_stats (h), 2 * sizeof (unsigned long long), cudaMemcpyDeviceToHost, h->stream));
 	CK (cudaStreamSynchronize (h->stream));
 	prof_resolve (h);
 	h->stats.d2h_bytes += bytes;
+	if (res[n_tab - 1] != 0) {
+		// Only reachable for a table that was handed out (phaserot_pending_table) and combined by the
+		// caller: this shard, or - the flag is part of the reduced buffer - some other rank's, overflowed
+		// its survivor list.  Every rank sees the same flag: each repeats its shard in dense mode on top of
+		// the combined table (a running maximum) and the caller reduces once more.
+		if (h->pend_again >= 2) {
+			snprintf (g_last_error, sizeof (g_last_error), "survivor list overflow flag still set after a dense repeat");
+			return PHASEROT_E_CUDA; // cannot happen: dense launches are sized to the list
+		}
+		++h->pend_again;
+		if (h->dense_mode && !h->pend_redone) {
+			// this rank's shard ran in dense mode and is complete; it was another rank's flag.  Clear the word
+			// and take part in the second reduction with the table as it is.
+			CK (cudaMemsetAsync (d_overflow (h), 0, sizeof (unsigned), h->stream));
+			return PHASEROT_E_AGAIN;
+		}
+		h->stats.points_evaluated += st[1];
+		h->dense_mode  = true;
+		h->pend_redone = true;
+		++h->stats.dense_repeats;
+		const phaserot::Redo r = h->redo;
+		rc = sweep_core (h, r.src, true, r.n_frames, r.t_end, r.first_block, r.hist, r.ang_start, r.ang_end, r.ang_stride, r.chn, PHASEROT_PCM_F32, true);
+		if (rc) return rc;
+		return PHASEROT_E_AGAIN;
+	}
 	for (int c = h->pend_c0; c < h->pend_c1; ++c) {
 		float* row = h->table.data () + (size_t)c * h->MS;
 		for (int k = 0; k < A; ++k) {
@@ -646,11 +690,17 @@ finish_pending (phaserot* h)
 		}
 	}
 	h->stats.points_evaluated += st[1];
+	if (getenv ("PHASEROT_DEBUG")) {
+		fprintf (stderr, "[phaserot] finish: listed %llu evaluated %llu points %llu dense %d cap %lld\n", st[0], st[1],
+		         (unsigned long long)h->pend_points, (int)h->dense_mode, h->list_cap);
+	}
 	// leave dense mode when the material no longer needs it (the list stayed far below the normal capacity)
-	if (h->dense_mode && !(h->cfg.flags & PHASEROT_FLAG_NO_PRUNE) && h->pend_points > 0 && (double)st[0] < 1e-3 * (double)h->pend_points) { // st[0]: points the lists held
+	// (judged on a dense pass that started from an empty table: a repeat starts from the peaks of the failed attempt and lists little)
+	if (h->dense_mode && !h->pend_redone && !(h->cfg.flags & PHASEROT_FLAG_NO_PRUNE) && h->pend_points > 0 && (double)st[0] < 1e-3 * (double)h->pend_points) { // st[0]: points the lists held
 		h->dense_mode = false;
 	}
-	h->pending = false;
+	h->pending      = false;
+	h->pend_exposed = false;
 	return PHASEROT_OK;
 }
 
@@ -719,7 +769,7 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 	}
 	rc = h->d_cs.ensure (sizeof (float2) * cs.size ());
 	if (rc) return rc;
-	rc = h->d_peaks.ensure (sizeof (unsigned) * ((size_t)std::max (A, 1) * h->C + (size_t)h->C));
+	rc = h->d_peaks.ensure (sizeof (unsigned) * ((size_t)std::max (A, 1) * h->C + (size_t)h->C + 1));
 	if (rc) return rc;
 	// staged through a pinned buffer of the handle: no synchronisation (the stream is
 	// idle with respect to the previous pass: finish_pending() above waited for it)
@@ -729,7 +779,9 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 	CK (cudaMemcpyAsync (h->d_cs.p, h->h_cs.p, sizeof (float2) * cs.size (), cudaMemcpyHostToDevice, h->stream));
 	h->pend_A = A; // d_raw() depends on it
 	if (!redo) {
-		CK (cudaMemsetAsync (h->d_peaks.p, 0, sizeof (unsigned) * ((size_t)std::max (A, 1) * h->C + (size_t)h->C), h->stream));
+		CK (cudaMemsetAsync (h->d_peaks.p, 0, sizeof (unsigned) * ((size_t)std::max (A, 1) * h->C + (size_t)h->C + 1), h->stream));
+	} else {
+		CK (cudaMemsetAsync (d_overflow (h), 0, sizeof (unsigned), h->stream)); // the repeat starts with a clear flag
 	}
 	CK (cudaMemsetAsync (h->d_small.p, 0, kSmallBytes, h->stream));
 	const bool no_prune = (h->cfg.flags & PHASEROT_FLAG_NO_PRUNE) != 0;
@@ -794,7 +846,9 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 		cap                 = std::min (std::max (segs_first, segs_max), std::max<long long> (nseg, 1)) * ppseg;
 	} else {
 		const long long full = std::min (std::max (segs_first, segs_max), std::max<long long> (nseg, 1)) * ppseg;
-		cap                  = std::min (full, std::max<long long> (1LL << 20, full / 32));
+		// (at least one wave: a stream too short for the bootstrap starts with an unpruned wave that lists every point)
+		const long long wave_pts = std::max<long long> (1, (h->n_sm + nchan - 1) / nchan) * ppseg;
+		cap                      = std::min (full, std::max ({ 1LL << 20, full / 32, wave_pts }));
 	}
 	const long long segs_cap = std::min (std::max (segs_first, segs_max), std::max<long long> (nseg, 1));
 	h->list_stride           = cap;
@@ -928,10 +982,20 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 		w.n_eval       = d_stats (h) + 1;
 		w.n_listed     = d_stats (h);
 		w.A            = A;
+		// a run of consecutive grid indices (the usual full sweep): slot = index - first, no table
+		w.slot_base = idx[0];
+		for (int k = 1; k < A; ++k) {
+			if (idx[(size_t)k] != idx[0] + k) {
+				w.slot_base = -1;
+				break;
+			}
+		}
+		const size_t wsm = (size_t)A * (sizeof (float2) + sizeof (unsigned));
+		w.smem_tables    = wsm <= 40 * 1024; // up to ~3400 angles (0.1 degree grid: 21 KB); finer grids read the tables through L1
 		{
 			ProfScope ps (h, 1);
 			sector_thr_kernel<<<dim3 (kSectors, (unsigned)nchan), 64, 0, h->stream>>> ((const unsigned*)h->d_peaks.p, A, (const int*)h->d_slot.p, h->MS, c0, (float*)h->d_sec.p);
-			sweep_window_kernel<<<dim3 ((unsigned)(h->n_sm * 8), (unsigned)nchan), 256, 0, h->stream>>> (w);
+			sweep_window_kernel<<<dim3 ((unsigned)(h->n_sm * 8), (unsigned)nchan), 256, w.smem_tables ? wsm : 0, h->stream>>> (w);
 		}
 		CK (cudaGetLastError ());
 		h->stats.kernel_launches += 2;
@@ -955,7 +1019,7 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 			tp.seg_jitter = p.seg_jitter;
 			tp.boot_beta  = boot ? kBootBeta : 0.f;
 			tp.list_cap   = boot ? (unsigned)std::min<long long> (h->list_cap, kBootCap) : (unsigned)h->list_cap;
-			tp.overflow   = boot ? d_overflow (h) + 1 : d_overflow (h);
+			tp.overflow   = boot ? d_overflow_ignored (h) : d_overflow (h);
 			{
 				ProfScope  ps (h, 6);
 				const dim3 grid ((unsigned)(n * (tp.V2 / kTpTile)), (unsigned)nchan);
@@ -973,11 +1037,10 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 			p.boot_beta   = boot ? kBootBeta : 0.f;
 			p.seg_jitter  = boot && stride > 1;
 			// the bootstrap wave only has to raise the running peaks (any subset of its points is
-			// valid, the contiguous passes visit the segments again): what does not fit a small
-			// list is dropped without flagging the pass - on constant-envelope material every
-			// point of the wave passes the gate, and 64 K of them already pin every angle
+			// valid, the contiguous passes visit the segments again): what does not fit kBootCap
+			// points is dropped without flagging the pass
 			p.list_cap    = boot ? (unsigned)std::min<long long> (h->list_cap, kBootCap) : (unsigned)h->list_cap;
-			p.overflow    = boot ? d_overflow (h) + 1 : d_overflow (h); // +1: a word nobody reads
+			p.overflow    = boot ? d_overflow_ignored (h) : d_overflow (h);
 			r = launch_conv<EPI_POINTS, SRC_INTER> (h, p);
 			if (r) return r;
 			r = sweep_survivors (p.count, p.list_cap, boot);
@@ -1066,7 +1129,7 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 		cudaGetLastError ();
 		if (!pinned) {
 			for (int b = 0; b < 2; ++b) {
-				rc = h->h_stage[b].ensure (bps * (size_t)chunk_frames * h->C);
+				rc = h->h_stage[b].ensure (bps * (size_t)std::min (chunk_frames, std::max<long long> (n_frames, 4)) * h->C); // short files: small staging (pinned allocation costs ~0.3 ms per MB)
 				if (rc) return rc;
 			}
 		}
@@ -1075,7 +1138,7 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 			// stream -> the float copy of the file; staging buffer b is reused two chunks
 			// later on the same stream, i.e. after the kernel that read it
 			for (int b = 0; b < 2; ++b) {
-				rc = h->d_stage[b].ensure (bps * (size_t)chunk_frames * h->C);
+				rc = h->d_stage[b].ensure (bps * (size_t)std::min (chunk_frames, std::max<long long> (n_frames, 4)) * h->C);
 				if (rc) return rc;
 			}
 		}
@@ -1129,6 +1192,9 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 		if (rc) return rc;
 	}
 	if (!redo) {
+		h->pend_again   = 0;
+		h->pend_exposed = false;
+		h->pend_redone  = false;
 		h->pend_points = (uint64_t)nchan * (uint64_t)(2 * (m_end - p.m_skip)) * (uint64_t)(OS > 1 ? OS + 1 : 1);
 		h->stats.points_total += h->pend_points;
 		// the device-resident form of this pass, should complete_pending() have to repeat it
@@ -1362,6 +1428,7 @@ phaserot_strerror (int code)
 		case PHASEROT_E_NOMEM: return "out of memory";
 		case PHASEROT_E_UNSUPPORTED: return "configuration not supported by the device path";
 		case PHASEROT_E_STATE: return "call not valid in this mode";
+		case PHASEROT_E_AGAIN: return "a shard of the combined sweep overflowed its survivor list: the pass has been re-enqueued in dense mode, combine the pending tables again";
 		default: return "unknown error";
 	}
 }
@@ -1795,13 +1862,7 @@ phaserot_pending_table (phaserot_t* h, float** d_table, int* n_channels, int* n_
 	if (!h->pending) {
 		return PHASEROT_E_STATE;
 	}
-	{
-		// the table handed out must be final for this shard: wait for the pass and repeat it
-		// in dense mode if its survivor list overflowed (see complete_pending())
-		DevGuard  guard (h->dev);
-		const int rc = complete_pending (h);
-		if (rc) return rc;
-	}
+	h->pend_exposed = true; // completion is now the caller's protocol, see the header
 	*d_table    = (float*)h->d_peaks.p;
 	*n_channels = h->C;
 	*n_angles   = std::max (h->pend_A, 1);
@@ -2427,7 +2488,7 @@ phaserot_group_sweep (phaserot_group_t* g, const void* data, int format, uint64_
 	// handles that got no shard keep an empty table
 	if (used > 1) {
 		DevGuard     guard (h0->dev);
-		const size_t cnt = (size_t)std::max (h0->pend_A, 1) * h0->C + (size_t)h0->C;
+		const size_t cnt = (size_t)std::max (h0->pend_A, 1) * h0->C + (size_t)h0->C + 1; // maxima, raw peaks, overflow flag (clear: every shard was completed above)
 		PeerTabs     pt;
 		pt.n = 0;
 		size_t n_copy = 0;

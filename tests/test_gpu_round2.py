@@ -252,7 +252,7 @@ def test_dense_mode_constant_envelope_equals_brute_force():
     dense mode (sector thresholds + per-point angle windows) and the table still equals brute force bit
     for bit; the handle stays dense for the same material and returns to normal mode on programme."""
     import torch
-    x = _tones(40.0, [(0.5, 440.0, [0.0, 1.0])])
+    x = _tones(100.0, [(0.5, 440.0, [0.0, 1.0])])     # 4.8 M points per channel against a list of 1.8 M
     xd = torch.from_numpy(x).cuda()
     with capi.Phaserot(n_channels=2, blksiz=8192, subsample=10, flags=capi.FLAG_NO_PRUNE) as hb:
         hb.sweep_device(xd.data_ptr(), x.shape[0])
@@ -278,7 +278,7 @@ def test_dense_mode_constant_envelope_equals_brute_force():
         h.sweep_shard(np.ascontiguousarray(x[cut:]), x.shape[0] - cut, x[cut - 8192:cut], False, True)
         assert np.array_equal(np.maximum(a, h.peaks()), brute)
         # programme material: the handle leaves dense mode again
-        prog = O.programme(48000, 40.0, 2)
+        prog = O.programme(48000, 60.0, 2)
         h.reset()
         h.sweep(prog)
         p1 = h.peaks()
@@ -334,3 +334,58 @@ def test_batch_render_per_track_angles():
             h.render_device(xd.data_ptr(), x.shape[0], ang, 1, yd.data_ptr())
             torch.cuda.synchronize()
             assert np.array_equal(yd.cpu().numpy(), y), i
+
+
+def test_sharded_overflow_protocol_e_again():
+    """Two 'ranks' (two handles) sweep the halves of a pure sine; their pending device tables are combined by
+    an element-wise max over the WHOLE buffers (what the NCCL max all-reduce does in place).  The overflow
+    flag of either shard is part of the buffer: both ranks get PHASEROT_E_AGAIN from peaks() after having
+    re-enqueued their shard in dense mode; one more combine gives the brute-force table on both."""
+    import torch
+    x = _tones(240.0, [(0.5, 440.0, [0.0, 1.0])])    # two shards of 5.8 M points per channel against lists of 1.8 M
+    xd = torch.from_numpy(x).cuda()
+    with capi.Phaserot(n_channels=2, blksiz=8192, subsample=10, flags=capi.FLAG_NO_PRUNE) as hb:
+        hb.sweep_device(xd.data_ptr(), x.shape[0])
+        brute = hb.peaks()
+    ranks = [capi.Phaserot(n_channels=2, blksiz=8192, subsample=10) for _ in range(2)]
+    try:
+        al = ranks[0].shard_align()
+        cut = al * ((x.shape[0] // 2) // al)
+        hist = xd[cut - 8192:cut].contiguous()
+
+        def views():
+            out = []
+            for h in ranks:
+                ptr, nc, na = h.pending_table()
+                n = nc * na + nc + 1
+
+                class _Dev:
+                    __cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+                out.append(torch.as_tensor(_Dev(), device="cuda"))
+            return out
+
+        def all_reduce_max():
+            torch.cuda.synchronize()          # the handles run on their own streams
+            a, b = views()
+            m = torch.maximum(a, b)
+            a.copy_(m)
+            b.copy_(m)
+            torch.cuda.synchronize()
+
+        ranks[0].sweep_shard_device(xd.data_ptr(), cut, None, True, False)
+        ranks[1].sweep_shard_device(xd[cut:].data_ptr(), x.shape[0] - cut, hist.data_ptr(), False, True)
+        all_reduce_max()
+        again = 0
+        for h in ranks:
+            with pytest.raises(capi.PhaserotError) as ei:
+                h.peaks()
+            assert ei.value.code == capi.E_AGAIN
+            again += 1
+        assert again == 2
+        all_reduce_max()
+        for h in ranks:
+            assert np.array_equal(h.peaks(), brute)
+            assert h.stats()["dense_repeats"] == 1
+    finally:
+        for h in ranks:
+            h.close()

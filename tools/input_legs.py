@@ -95,6 +95,7 @@ if __name__ == "__main__":
     ap.add_argument("--check", action="store_true", help="compare every pruned table with brute force (bit for bit)")
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
+    torch.cuda.set_stream(torch.cuda.Stream(device=dev))  # an explicit stream: handle 0 means "private stream" to phaserot_set_stream
     frames = int(a.seconds * bench.SR)
     frames -= frames % (32768 - bench.BLKSIZ)
     n_chunks = (frames + bench.GEN_CHUNK - 1) // bench.GEN_CHUNK

@@ -22,6 +22,7 @@ import bench  # noqa: E402
 from phaserotate.lv2_b200 import build, capi  # noqa: E402
 
 dev = torch.device("cuda", 0)
+torch.cuda.set_stream(torch.cuda.Stream(device=dev))  # an explicit stream: handle 0 means "private stream" to phaserot_set_stream
 GEN = 1 << 21
 
 

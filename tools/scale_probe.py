@@ -14,6 +14,7 @@ from phaserotate.lv2_b200 import capi  # noqa: E402
 world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
+torch.cuda.set_stream(torch.cuda.Stream(device=dev))  # an explicit stream: handle 0 means "private stream" to phaserot_set_stream
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 frames = int(3600 * bench.SR); frames -= frames % (32768 - bench.BLKSIZ)
@@ -29,7 +30,7 @@ def table():
     ptr, nc, na = h.pending_table()
 
     class _D:
-        __cuda_array_interface__ = {"shape": (nc * na + nc,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+        __cuda_array_interface__ = {"shape": (nc * na + nc + 1,), "typestr": "<f4", "data": (ptr, False), "version": 2}
     return torch.as_tensor(_D(), device=dev)
 
 
