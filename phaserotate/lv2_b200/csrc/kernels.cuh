@@ -101,6 +101,7 @@ struct ConvParams {
 	float*        out_inter;    // EPI_RENDER: interleaved destination [out_frames][C] instead of `out` (fused CLI render)
 	long long     out_frames;
 	int           out_compact;  // EPI_HILBERT: segment j of the launch writes its V outputs at out[8 + j V ..) (true-peak staging)
+	int           prefetch;     // > 0: L2 prefetch distance in segments (experiments; 0 = off, the default)
 };
 
 // Segment input loaders: z[n0 + idx] for the first forward pass and the direct
@@ -631,9 +632,19 @@ __global__ void __launch_bounds__ (kConvThreads, 1) fftconv_kernel (const ConvPa
 				spectrum_only (sm, xch, p.tw1, p.tw2, p.scratch + (size_t)blockIdx.x * (kM / 2), tid, EdgeLoader { p.inter, p.hist, p.n_frames, 2 * (n0 - p.V), p.C, c, p.hist_frames });
 			}
 		}
-		// (No L2 prefetch of the next segment: a cp.async.bulk.prefetch.L2 of the stretch one
+		// (No L2 prefetch of the next segment by default: a cp.async.bulk.prefetch.L2 of the stretch one
 		// segment ahead made the long launches read 1.26x their bytes from HBM - the lines were
-		// fetched, evicted and fetched again - and was 1 % slower than plain loads; r02 traffic probe.)
+		// fetched, evicted and fetched again - and was 1 % slower than plain loads; r02 traffic probe.
+		// p.prefetch = d > 0 prefetches the new part of segment si + d instead, for experiments.)
+		if (p.prefetch > 0 && SRC == SRC_INTER && p.seg_stride == 1 && si + p.prefetch < s_end && lane == 0 && ci == 0) {
+			const long long nn0    = n0 + (long long)p.prefetch * p.V + p.Lh;
+			const long long nbytes = (nn0 >= 0 && 2 * (nn0 + p.V) <= p.n_frames) ? (long long)p.V * 2 * p.C * (long long)sizeof (float) : 0;
+			if (nbytes > 0) {
+				const unsigned piece = (unsigned)(nbytes >> 4) & ~15u;
+				const char*    a     = reinterpret_cast<const char*> (reinterpret_cast<uintptr_t> (p.inter + 2 * nn0 * p.C) & ~(uintptr_t)15) + (size_t)(tid >> 5) * piece;
+				asm volatile ("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a), "r"(piece) : "memory");
+			}
+		}
 
 		// local bounds of the output regions (clamped to the segment)
 		cx.c     = c;

@@ -391,6 +391,7 @@ fill_conv_common (phaserot* h, ConvParams& p)
 	p.G1           = (const float2*)h->d_G1.p;
 	p.scratch      = (float4*)h->d_scratch.p;
 	p.seg_stride   = 1;
+	p.prefetch     = getenv ("PHASEROT_PREFETCH") ? atoi (getenv ("PHASEROT_PREFETCH")) : 0;
 }
 
 // Function attributes are per device (per context): phaserot_create() sets them

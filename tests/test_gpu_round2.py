@@ -263,7 +263,7 @@ def test_dense_mode_constant_envelope_equals_brute_force():
         st = h.stats()
         assert st["dense_repeats"] == 1
         assert np.array_equal(got, brute)
-        assert st["points_evaluated"] < 0.1 * st["points_total"]      # windows, not every angle
+        assert st["points_evaluated"] < 0.5 * st["points_total"]      # the bootstrap wave is swept at every angle (<= 1 M points per channel), the rest in windows
         h.reset()
         h.sweep_device(xd.data_ptr(), x.shape[0])                     # sticky: no second repeat
         assert np.array_equal(h.peaks(), brute)
