@@ -819,7 +819,10 @@ __global__ void __launch_bounds__ (256) sweep_kernel (const float2* __restrict__
 	const int       c    = chan0 + blockIdx.z;
 	if (skip_overflowed && count[c] > cap) return;  // the pass is flagged and will be repeated in dense mode: do not brute-force a full list first
 	const unsigned  n    = min (count[c], cap); // (bootstrap wave: the counter may run past its small capacity, the excess was dropped)
-	if (blockIdx.x * kSweepTile >= n) return; // most launches see a few dozen survivors: nothing for this CTA
+	// Short lists (the usual case: a few hundred survivors per launch) are cut into small tiles so that
+	// many CTAs share them: one CTA walking a 256-point tile alone is a 10 us serial chain.
+	const unsigned tile_pts = min ((unsigned)kSweepTile, max (32u, ((n + gridDim.x - 1) / gridDim.x + 1) & ~1u));
+	if (blockIdx.x * tile_pts >= n) return; // nothing for this CTA
 	const float2*   pts  = list + (long long)c * list_stride;
 	const int       a0   = blockIdx.y * (blockDim.x * R) + threadIdx.x;
 
@@ -833,10 +836,10 @@ __global__ void __launch_bounds__ (256) sweep_kernel (const float2* __restrict__
 		pk[r] = 0.f;
 	}
 
-	for (unsigned base = blockIdx.x * kSweepTile; base < n; base += gridDim.x * kSweepTile) {
-		const unsigned cnt = min ((unsigned)kSweepTile, n - base);
+	for (unsigned base = blockIdx.x * tile_pts; base < n; base += gridDim.x * tile_pts) {
+		const unsigned cnt = min (tile_pts, n - base);
 		__syncthreads ();
-		for (unsigned i = threadIdx.x; i < kSweepTile; i += blockDim.x) {
+		for (unsigned i = threadIdx.x; i < tile_pts; i += blockDim.x) {
 			tile[i] = i < cnt ? pts[base + i] : make_float2 (0.f, 0.f);
 		}
 		__syncthreads ();
