@@ -187,6 +187,20 @@ PHASEROT_API int phaserot_sweep_shard_device (phaserot_t* h, const float* d_inte
                                               const float* hist, int first, int last,
                                               int ang_start, int ang_end, int ang_stride, int chn);
 
+/* Two-phase form of phaserot_sweep_shard_device() for strong scaling (many ranks, each with a small
+ * part of one stream).  A rank that bootstraps its filter radius from its own shard only prunes
+ * against the peaks of that shard, which can be far below those of the whole stream: more survivors,
+ * more sweep work, and the step waits for the worst rank.  Split the call:
+ *     phaserot_sweep_shard_boot_device (h, ...);    enqueue the bootstrap wave of this shard only
+ *     phaserot_pending_table + max all-reduce       the union of all ranks' waves = a sparse sample of the WHOLE stream
+ *     phaserot_sweep_shard_resume (h);              the contiguous passes, pruning with the combined thresholds
+ *     phaserot_pending_table + max all-reduce + phaserot_peaks   as for the one-call form
+ * The result is the same table bit for bit (a running maximum; pruning is exact either way). */
+PHASEROT_API int phaserot_sweep_shard_boot_device (phaserot_t* h, const float* d_interleaved, uint64_t n_frames,
+                                                   const float* hist, int first, int last,
+                                                   int ang_start, int ang_end, int ang_stride, int chn);
+PHASEROT_API int phaserot_sweep_shard_resume (phaserot_t* h);
+
 /* The same shard from HOST memory (`data`: interleaved, `format` = PHASEROT_PCM_*;
  * pinned is faster): uploaded in chunks on a copy stream while the compute stream
  * works on what has landed, like phaserot_sweep().  `hist`: blksiz frames of

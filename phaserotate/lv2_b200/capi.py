@@ -25,6 +25,7 @@ SYMBOLS = [
     "phaserot_apply", "phaserot_render", "phaserot_render_device",
     "phaserot_process", "phaserot_process_levels", "phaserot_latency",
     "phaserot_sweep_shard_device", "phaserot_sweep_shard", "phaserot_shard_align", "phaserot_plugin_angle",
+    "phaserot_sweep_shard_boot_device", "phaserot_sweep_shard_resume",
     "phaserot_group_create", "phaserot_group_destroy", "phaserot_group_size", "phaserot_group_handle", "phaserot_group_sweep",
     "phaserot_group_peaks", "phaserot_group_reset", "phaserot_pending_table", "phaserot_set_profiling", "phaserot_get_kernel_times",
     "phaserot_sync", "phaserot_get_stats", "phaserot_reset_stats",
@@ -100,6 +101,8 @@ def load():
     lib.phaserot_sweep_shard_device.argtypes = [vp, vp, C.c_uint64, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.phaserot_sweep_shard.argtypes = [vp, vp, C.c_int, C.c_uint64, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     lib.phaserot_plugin_angle.argtypes = [vp, vp]
+    lib.phaserot_sweep_shard_boot_device.argtypes = [vp, vp, C.c_uint64, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    lib.phaserot_sweep_shard_resume.argtypes = [vp]
     lib.phaserot_group_create.argtypes = [C.POINTER(vp), C.POINTER(Cfg), vp, C.c_int]
     lib.phaserot_group_destroy.argtypes = [vp]
     lib.phaserot_group_destroy.restype = None
@@ -242,6 +245,23 @@ class Phaserot:
             hp = _ptr(hist)
         self._ck(self._lib.phaserot_sweep_shard_device(self._h, C.c_void_p(dev_ptr), n_frames, hp, int(first), int(last),
                                                        ang_start, ang_end, stride, chn), "phaserot_sweep_shard_device")
+
+    def sweep_shard_boot_device(self, dev_ptr, n_frames, hist, first, last, ang_start=0, ang_end=None, stride=1, chn=-1):
+        """Phase 1 of the two-phase sharded sweep: the bootstrap wave only (hist like sweep_shard_device)."""
+        if ang_end is None:
+            ang_end = self.maxsample
+        hp = None
+        if isinstance(hist, int):
+            hp = C.c_void_p(hist)
+        elif hist is not None:
+            hist = np.ascontiguousarray(hist, np.float32)
+            hp = _ptr(hist)
+        self._ck(self._lib.phaserot_sweep_shard_boot_device(self._h, C.c_void_p(dev_ptr), n_frames, hp, int(first), int(last),
+                                                            ang_start, ang_end, stride, chn), "phaserot_sweep_shard_boot_device")
+
+    def sweep_shard_resume(self):
+        """Phase 2: the contiguous passes on top of the (combined) pending table."""
+        self._ck(self._lib.phaserot_sweep_shard_resume(self._h), "phaserot_sweep_shard_resume")
 
     def pending_table(self):
         """(device pointer, n_channels, n_angles) of the pending sweep's table: n_channels * n_angles + n_channels + 1 floats

@@ -579,7 +579,7 @@ launch_sweep (phaserot* h, int A, int c0, int nchan, const unsigned* count, cons
 }
 
 int sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frames, long long t_end, bool first_block, const float* hist,
-                int ang_start, int ang_end, int ang_stride, int chn, int fmt, bool redo);
+                int ang_start, int ang_end, int ang_stride, int chn, int fmt, bool redo, bool boot_only);
 
 // The pending sweep is complete on the device when this returns: waits for it and,
 // if a survivor list overflowed (material where most samples survive the radius
@@ -615,7 +615,7 @@ complete_pending (phaserot* h)
 		h->pend_redone = true;
 		++h->stats.dense_repeats;
 		const phaserot::Redo r = h->redo;
-		rc = sweep_core (h, r.src, true, r.n_frames, r.t_end, r.first_block, r.hist, r.ang_start, r.ang_end, r.ang_stride, r.chn, PHASEROT_PCM_F32, true);
+		rc = sweep_core (h, r.src, true, r.n_frames, r.t_end, r.first_block, r.hist, r.ang_start, r.ang_end, r.ang_stride, r.chn, PHASEROT_PCM_F32, true, false);
 		if (rc) return rc;
 	}
 	return PHASEROT_OK;
@@ -672,7 +672,7 @@ finish_pending (phaserot* h)
 		h->pend_redone = true;
 		++h->stats.dense_repeats;
 		const phaserot::Redo r = h->redo;
-		rc = sweep_core (h, r.src, true, r.n_frames, r.t_end, r.first_block, r.hist, r.ang_start, r.ang_end, r.ang_stride, r.chn, PHASEROT_PCM_F32, true);
+		rc = sweep_core (h, r.src, true, r.n_frames, r.t_end, r.first_block, r.hist, r.ang_start, r.ang_end, r.ang_stride, r.chn, PHASEROT_PCM_F32, true, false);
 		if (rc) return rc;
 		return PHASEROT_E_AGAIN;
 	}
@@ -745,7 +745,8 @@ angle_schedule (phaserot* h, int ang_start, int ang_end, int ang_stride, std::ve
 int
 sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frames, long long t_end, bool first_block,
             const float* hist, int ang_start, int ang_end, int ang_stride, int chn, int fmt = PHASEROT_PCM_F32 /* host src: PHASEROT_PCM_* */,
-            bool redo = false /* dense-mode repeat of the pending sweep: keep the device table */)
+            bool redo = false /* repeat / continuation of the pending sweep: keep the device table, no bootstrap */,
+            bool boot_only = false /* enqueue the bootstrap wave and its sweep only (two-phase sharded sweep) */)
 {
 	// bytes per sample on the host side (and on the bus); 0 = float32, no conversion pass
 	const int pcm_bytes = fmt == PHASEROT_PCM_S16 ? 2 : fmt == PHASEROT_PCM_S32 ? 4 : fmt == PHASEROT_PCM_S24 ? 3 : 0;
@@ -1093,8 +1094,12 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 			if (r) return r;
 			booted = true;
 		}
-		while (seg_done < seg_ready) {
-			const long long want = !booted ? wave : (n_main == 0 ? segs_first : segs_max);
+		while (!boot_only && seg_done < seg_ready) {
+			// first contiguous launch: 8 segments per CTA as a refresh of the radius - unless what would be
+			// left for the second launch is less than that (short streams, shards of a strong-scaling run):
+			// then everything goes into one launch and a launch + sweep round trip (~35 us) is saved
+			const bool      short_rest = src_is_device && final && nseg - seg_done <= 2 * segs_first;
+			const long long want       = !booted ? wave : ((n_main == 0 && !short_rest) ? segs_first : segs_max);
 			const long long n    = std::min (want, seg_ready - seg_done);
 			if (!final && n < want && seg_ready < nseg) {
 				break; // wait for more data to keep launches full
@@ -1817,6 +1822,40 @@ phaserot_sweep_shard_device (phaserot_t* h, const float* d_interleaved, uint64_t
 	const long long B     = (F + h->L - 1) / h->L;
 	const long long t_end = last ? (B + 1) * h->L : F;
 	return sweep_core (h, d_interleaved, true, F, t_end, first != 0 && B > 0, hist, ang_start, ang_end, ang_stride, chn);
+}
+
+int
+phaserot_sweep_shard_boot_device (phaserot_t* h, const float* d_interleaved, uint64_t n_frames, const float* hist, int first, int last,
+                                  int ang_start, int ang_end, int ang_stride, int chn)
+{
+	if (!h || (!d_interleaved && n_frames)) {
+		return PHASEROT_E_INVAL;
+	}
+	if (h->plugin) {
+		return PHASEROT_E_STATE;
+	}
+	const long long F = (long long)n_frames;
+	if (!last && (F % h->L) != 0) {
+		return PHASEROT_E_INVAL;
+	}
+	DevGuard        guard (h->dev);
+	const long long B     = (F + h->L - 1) / h->L;
+	const long long t_end = last ? (B + 1) * h->L : F;
+	return sweep_core (h, d_interleaved, true, F, t_end, first != 0 && B > 0, hist, ang_start, ang_end, ang_stride, chn, PHASEROT_PCM_F32, false, true);
+}
+
+int
+phaserot_sweep_shard_resume (phaserot_t* h)
+{
+	if (!h) {
+		return PHASEROT_E_INVAL;
+	}
+	if (h->plugin || !h->pending) {
+		return PHASEROT_E_STATE;
+	}
+	DevGuard              guard (h->dev);
+	const phaserot::Redo r = h->redo;
+	return sweep_core (h, r.src, true, r.n_frames, r.t_end, r.first_block, r.hist, r.ang_start, r.ang_end, r.ang_stride, r.chn, PHASEROT_PCM_F32, true, false);
 }
 
 int

@@ -389,3 +389,60 @@ def test_sharded_overflow_protocol_e_again():
     finally:
         for h in ranks:
             h.close()
+
+
+def test_two_phase_sharded_sweep_equals_single_pass():
+    """phaserot_sweep_shard_boot_device + phaserot_sweep_shard_resume: the ranks' bootstrap waves are combined
+    (max over the pending tables) before the contiguous passes, so every rank prunes with the thresholds of the
+    whole stream's sample.  Same table as the single pass, bit for bit; fewer survivors than shards that each
+    bootstrap on their own."""
+    import torch
+    x = O.programme(48000, 300.0, 2)
+    x[: x.shape[0] // 2] *= 0.25                      # a quiet first half: its own bootstrap would prune poorly
+    xd = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    with capi.Phaserot(n_channels=2, blksiz=8192, subsample=10) as h:
+        h.sweep_device(xd.data_ptr(), x.shape[0])
+        whole = h.peaks()
+        al = h.shard_align()
+    cut = al * ((x.shape[0] // 2) // al)
+    hist = xd[cut - 8192:cut].contiguous()
+    shards = [(xd.data_ptr(), cut, None, True, False), (xd[cut:].data_ptr(), x.shape[0] - cut, hist.data_ptr(), False, True)]
+
+    def run(two_phase):
+        ranks = [capi.Phaserot(n_channels=2, blksiz=8192, subsample=10) for _ in range(2)]
+        try:
+            def all_reduce_max():
+                torch.cuda.synchronize()
+                v = []
+                for h in ranks:
+                    ptr, nc, na = h.pending_table()
+
+                    class _Dev:
+                        __cuda_array_interface__ = {"shape": (nc * na + nc + 1,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+                    v.append(torch.as_tensor(_Dev(), device="cuda"))
+                m = torch.maximum(v[0], v[1])
+                v[0].copy_(m)
+                v[1].copy_(m)
+                torch.cuda.synchronize()
+            if two_phase:
+                for h, s in zip(ranks, shards):
+                    h.sweep_shard_boot_device(*s)
+                all_reduce_max()
+                for h in ranks:
+                    h.sweep_shard_resume()
+            else:
+                for h, s in zip(ranks, shards):
+                    h.sweep_shard_device(*s)
+            all_reduce_max()
+            tabs = [h.peaks() for h in ranks]
+            ev = sum(h.stats()["points_evaluated"] for h in ranks)
+            return tabs, ev
+        finally:
+            for h in ranks:
+                h.close()
+
+    t1, ev1 = run(False)
+    t2, ev2 = run(True)
+    for t in t1 + t2:
+        assert np.array_equal(t, whole)
+    assert ev2 <= ev1
