@@ -1081,6 +1081,146 @@ __global__ void __launch_bounds__ (256) sweep_window_kernel (const WinParams p)
 	}
 }
 
+// The same sweep when the swept set is the whole grid, or all of it but an angle or two (the CLI's sweep leaves
+// out angle 0; slot = grid index - slot_base), without a single acos: |y_j| = r |cos (alpha_j - phi)| falls monotonically with the distance of j from the direction of the
+// point, out to 90 degrees on either side.  The thread evaluates the grid angle nearest to phi, then walks
+// outwards in both directions: every visited angle is evaluated (sweep_kernel's fp32 expression) and compared
+// with the running peak; the walk
+//   * stops for good when |y_j| falls below the global threshold (the smallest sector threshold): no angle
+//     farther out can be raised;
+//   * jumps to the near edge of the next sector when |y_j| falls below the threshold of the sector j lies in:
+//     no angle farther out IN THAT SECTOR can be raised.
+// A point of a constant-envelope signal costs one atan2 and the handful of angles within reach of its own
+// sector's threshold; an interior point of a two-tone signal one evaluation per sector within reach of the
+// global threshold.  Margins: 4e-6 relative on every threshold and 2e-6 r absolute on every comparison (the fp32
+// evaluation of y is good to ~3e-7 r, so a value farther out can exceed the one that stopped the walk by at most
+// 6e-7 r); the walk starts one step beyond the nearest grid angle on either side, and the nearest grid angle is
+// found to 2e-5 rad (atan2_fast) + one rounding - far less than half a step for every grid whose tables fit
+// shared memory (the condition for this kernel; finer grids keep sweep_window_kernel).
+// MUFU.RCP / one instruction
+__device__ __forceinline__ float rcp_approx (float x)
+{
+	float r;
+	asm ("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return r;
+}
+
+template <int WH> // half width of the window every point starts with, in grid angles
+__global__ void __launch_bounds__ (256) sweep_walk_kernel (const WinParams p)
+{
+	const int      c = p.chan0 + blockIdx.y;
+	const unsigned n = min (p.count[c], p.cap);
+	const int      MS = p.MS, G = MS / kSectors;
+	const float    inv_step = (float)MS / 3.14159265358979f, inv_G = 1.f / (float)G;
+	unsigned*      pk = p.peaks + (long long)c * p.peaks_stride;
+	// (ca, sa, snapshot of the running peak, -) per angle in shared memory, one LDS.128 per evaluation.  The
+	// snapshot only lags behind the table, so a stale value costs an atomic, never a maximum.
+	extern __shared__ __align__ (16) unsigned char win_sm[];
+	float4* s_tab = reinterpret_cast<float4*> (win_sm);
+	for (int k = threadIdx.x; k < p.A; k += blockDim.x) {
+		const float2 w = p.cs[k];
+		s_tab[k]       = make_float4 (w.x, w.y, __uint_as_float (pk[k]), 0.f);
+	}
+	__shared__ float s_sec[kSectors + 4];
+	if (threadIdx.x < kSectors) s_sec[threadIdx.x] = p.sec[c * kSectors + threadIdx.x] * (1.f - 4e-6f);
+	__syncthreads ();
+	if (threadIdx.x < 32) {
+		float m = fminf (s_sec[threadIdx.x], threadIdx.x + 32 < kSectors ? s_sec[threadIdx.x + 32] : __int_as_float (0x7f800000));
+		for (int o = 16; o; o >>= 1) m = fminf (m, __shfl_xor_sync (0xffffffffu, m, o));
+		if (threadIdx.x == 0) s_sec[kSectors] = m;
+	}
+	__syncthreads ();
+	const float tg = s_sec[kSectors];
+	if (!(tg < __int_as_float (0x7f800000))) return;
+	if (blockIdx.x == 0 && threadIdx.x == 0 && p.n_listed) atomicAdd (p.n_listed, (unsigned long long)n);
+	auto eval = [&] (const float2& q, int k) -> float {
+		const float4 w = s_tab[k];
+		const float  y = fabsf (fmaf (w.x, q.x, w.y * q.y)); // sweep_kernel's expression
+		if (y > w.z) {                                        // (peaks are never negative and never NaN: the same order as their bit patterns)
+			atomicMax (reinterpret_cast<unsigned*> (&s_tab[k].z), __float_as_uint (y));
+			atomicMax (pk + k, __float_as_uint (y));
+		}
+		return y;
+	};
+	unsigned       evals  = 0;
+	const unsigned stride = gridDim.x * blockDim.x;
+	// whole warps per trip, reconverged at the top: a thread that leaves the rare walk below late must not
+	// drag its warp through the next point's window once more on its own
+	for (unsigned base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
+		__syncwarp ();
+		const unsigned i  = base + (threadIdx.x & 31u);
+		const float2   q  = i < n ? p.list[(long long)c * p.list_stride + i] : make_float2 (0.f, 0.f);
+		const float    ax = fabsf (q.x), ay = fabsf (q.y);
+		const float    tgs = fmaf (-2e-6f, ax + ay, tg); // global threshold less the slack of a comparison (2e-6 r at least)
+		// nearest grid angle: alpha = phi (mod pi)  <=>  j = -phi / step (mod MS); atan2 as in atan2_fast()
+		const float mx = fmaxf (ax, ay), mn = fminf (ax, ay);
+		const float z  = mn * rcp_approx (fmaxf (mx, 1e-30f));
+		const float z2 = z * z;
+		float       pl = fmaf (-0.0117212f, z2, 0.05265332f);
+		pl             = fmaf (pl, z2, -0.11643287f);
+		pl             = fmaf (pl, z2, 0.19354346f);
+		pl             = fmaf (pl, z2, -0.33262347f);
+		pl             = fmaf (pl, z2, 0.99997726f);
+		float a        = z * pl;
+		if (ay > ax) a = 1.57079632679f - a;
+		if (q.x < 0.f) a = 3.14159265359f - a;
+		if (q.y >= 0.f) a = -a; // -phi
+		int j0 = __float2int_rn (a * inv_step);
+		if (j0 < 0) j0 += MS;
+		if (j0 >= MS) j0 -= MS;
+		// A window of 2 WH + 1 angles around j0 first, the same for every thread of the warp (no branch but the
+		// rare atomic): for a point of a constant-envelope signal - r a few 1e-6 above the threshold - both ends
+		// of it already lie below the global threshold and that is all there is.  (Near the ends of the table the
+		// window is pushed inside - any evaluation is a valid one - and both walks start at distance 1.)
+		const int k0 = j0 - p.slot_base;
+		const int kc = min (max (k0, WH), p.A - 1 - WH);
+		float     yl = 0.f, yr = 0.f;
+#pragma unroll
+		for (int t = -WH; t <= WH; ++t) {
+			const float y = eval (q, kc + t);
+			if (t == -WH) yl = y;
+			if (t == WH) yr = y;
+		}
+		int  done = 2 * WH + 1;
+		bool wide = false;
+		if (mx > 0.f && (kc != k0 || yl >= tgs || yr >= tgs)) { // rare
+#pragma unroll 1
+			for (int dir = 0; dir < 2; ++dir) {
+				const int room = dir ? (MS - 1) / 2 : MS / 2; // angles ahead out to 90 degrees
+				int       t    = kc != k0 ? 1 : ((dir ? yl : yr) >= tgs ? WH + 1 : MS);
+				while (t <= room) {
+					int j = dir ? j0 - t : j0 + t; // distance t from j0
+					if (j < 0) j += MS;
+					if (j >= MS) j -= MS;
+					const int k = j - p.slot_base;
+					const int s = __float2int_rd (((float)j + 0.5f) * inv_G); // sector of j
+					float     y = __int_as_float (0x7f800000); // not swept (the CLI leaves out angle 0): nothing to evaluate, nothing learnt
+					if (k >= 0 && k < p.A) y = eval (q, k);
+					++done;
+					if (!(y >= tgs)) break;
+					// within reach of the sector's threshold: next angle; else on to the near edge of the next sector
+					t += (y >= s_sec[s] - (tg - tgs)) ? 1 : (dir ? j - s * G + 1 : (s + 1) * G - j);
+					if (done > kWideEvals) break;
+				}
+				if (done > kWideEvals) {
+					wide = true; // what has been evaluated stays valid (a running maximum); the point is redone whole
+					break;
+				}
+			}
+		}
+		evals += i < n ? (unsigned)done : 0u;
+		if (wide) {
+			const unsigned at = atomicAdd (p.wide_count + c, 1u);
+			p.wide[(long long)c * p.wide_stride + at] = q; // the wide list has the capacity of the list itself
+		}
+	}
+	if (p.n_eval) {
+		unsigned long long e = evals;
+		for (int o = 16; o; o >>= 1) e += __shfl_xor_sync (0xffffffffu, e, o);
+		if ((threadIdx.x & 31) == 0 && e) atomicAdd (p.n_eval, (e + (unsigned long long)p.A - 1) / (unsigned long long)p.A);
+	}
+}
+
 // (ca, sa) of the plugin's small-call path: output i of channel c uses
 // pre[c][i] for i < rlen[c] (angle ramp, src:673-709) and cs[c] after that.
 struct FirCoef {

@@ -837,9 +837,10 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 	// largest launch (pruning leaves 1e-4 .. 1e-5 of them on programme material), at
 	// least 1 M points per channel; a list that overflows flags the pass and
 	// complete_pending() repeats it in dense mode.  Dense mode (and NO_PRUNE, where
-	// every point goes on the list): at most kDenseCap points per channel, and the
+	// every point goes on the list): at most kDenseCap points per channel (4 M .. 48 M), and the
 	// launches are sized to it, so nothing can overflow.
-	constexpr long long kDenseCap = 16LL << 20;
+	// (the list and the wide list: 16 bytes per point and channel; 2 GB between them, 48 M points for stereo)
+	const long long kDenseCap = std::min<long long> (48LL << 20, std::max<long long> (4LL << 20, (2LL << 30) / (16LL * std::max (1, nchan))));
 	long long           cap;
 	if (dense) {
 		const long long fit = std::max<long long> (1, kDenseCap / ppseg);
@@ -997,7 +998,21 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 		{
 			ProfScope ps (h, 1);
 			sector_thr_kernel<<<dim3 (kSectors, (unsigned)nchan), 64, 0, h->stream>>> ((const unsigned*)h->d_peaks.p, A, (const int*)h->d_slot.p, h->MS, c0, (float*)h->d_sec.p);
-			sweep_window_kernel<<<dim3 ((unsigned)(h->n_sm * 8), (unsigned)nchan), 256, w.smem_tables ? wsm : 0, h->stream>>> (w);
+			static const int walk = getenv ("PHASEROT_WALK") ? atoi (getenv ("PHASEROT_WALK")) : 1;
+			if (walk && (size_t)A * sizeof (float4) <= 44 * 1024 && w.slot_base >= 0 && A + 2 >= h->MS && A >= 64) { // (nearly) the whole grid: a window around the direction of the point, then walk outwards
+				const dim3 wg ((unsigned)(h->n_sm * 8), (unsigned)nchan);
+				static const double wrad = getenv ("PHASEROT_WALK_RAD") ? atof (getenv ("PHASEROT_WALK_RAD")) : 5e-3;
+				const int  wh = (int)ceil (wrad * h->MS / M_PI); // half width of the first window: 5e-3 rad in grid angles (reaches points up to 7e-6 above the threshold)
+				const size_t tsm = (size_t)A * sizeof (float4);
+				if (wh <= 1) sweep_walk_kernel<1><<<wg, 256, tsm, h->stream>>> (w);
+				else if (wh <= 2) sweep_walk_kernel<2><<<wg, 256, tsm, h->stream>>> (w);
+				else if (wh <= 3) sweep_walk_kernel<3><<<wg, 256, tsm, h->stream>>> (w);
+				else if (wh <= 4) sweep_walk_kernel<4><<<wg, 256, tsm, h->stream>>> (w);
+				else if (wh <= 6) sweep_walk_kernel<6><<<wg, 256, tsm, h->stream>>> (w);
+				else sweep_walk_kernel<8><<<wg, 256, tsm, h->stream>>> (w);
+			} else {
+				sweep_window_kernel<<<dim3 ((unsigned)(h->n_sm * 8), (unsigned)nchan), 256, w.smem_tables ? wsm : 0, h->stream>>> (w);
+			}
 		}
 		CK (cudaGetLastError ());
 		h->stats.kernel_launches += 2;

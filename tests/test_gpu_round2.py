@@ -297,6 +297,55 @@ def test_dense_mode_constant_envelope_equals_brute_force():
         assert np.max(np.abs(h.peaks() - po) / po) <= 1e-5
 
 
+@pytest.mark.parametrize("subsample,nch", [(1, 2), (4, 1), (10, 2), (20, 2), (50, 1)])
+@pytest.mark.parametrize("material", ["faded_sine", "two_tone", "chirp"])
+def test_dense_mode_grids_and_envelopes(subsample, nch, material):
+    """Dense mode over the grids that select the different window kernels (0.05 degree and coarser: the
+    walk kernel with a first window of 1 / 2 / 3 / 6 angles either side; 0.02 degree: tables too large for
+    shared memory, the sector-window kernel) and over materials that stress different parts of it: a sine
+    that fades in and out (flat peak table: every point within 1e-6 of every threshold, the first window is
+    all there is), BASELINE config 1's two tones (interior points well above the smallest threshold: the
+    walk from sector to sector), a slow chirp (constant envelope, directions not periodic).  Long enough to
+    overflow the survivor list (mono needs more than the 148-segment first wave); every table equals brute
+    force bit for bit."""
+    import torch
+    sr  = 48000
+    secs = 100.0 if nch == 2 else 240.0
+    n = int(sr * secs)
+    t = np.arange(n, dtype=np.float64) / sr
+    if material == "faded_sine":
+        parts = [(0.5 * np.minimum(1.0, np.minimum(t, secs - t) / 2.0), 2 * np.pi * 440.0 * t, 0.9)]
+    elif material == "two_tone":
+        parts = [(0.5, 2 * np.pi * 110.0 * t, 1.0), (0.25, 2 * np.pi * 1760.3 * t, 0.0)]
+    else:
+        parts = [(0.5, 2 * np.pi * (300.0 * t + 0.5 * (200.0 / secs) * t * t), 0.9)]      # 300 Hz -> 500 Hz
+    def render(parts):
+        return np.stack([sum(a * np.sin(ph + dph * c) for a, ph, dph in parts).astype(np.float32) for c in range(nch)], axis=1)
+    x = render(parts)
+    xd = torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    with capi.Phaserot(n_channels=nch, blksiz=8192, subsample=subsample, flags=capi.FLAG_NO_PRUNE) as hb:
+        hb.sweep_device(xd.data_ptr(), n)
+        brute = hb.peaks()
+    with capi.Phaserot(n_channels=nch, blksiz=8192, subsample=subsample) as h:
+        if material == "two_tone":
+            # a tenth of its samples survive the radius filter: not enough to overflow the list by itself, plenty
+            # to keep a handle dense that is (sticky until the lists hold < 0.1 % of the samples)
+            sd = torch.from_numpy(render([(0.5, 2 * np.pi * 440.0 * t, 0.9)])).cuda()
+            h.sweep_device(sd.data_ptr(), n)
+            h.peaks()
+            assert h.stats()["dense_repeats"] == 1
+            h.reset()
+        h.sweep_device(xd.data_ptr(), n)
+        got = h.peaks()
+        st = h.stats()
+        assert np.array_equal(got, brute), st
+        assert st["dense_repeats"] == 1, ("the material was meant to overflow the survivor list", st)
+        h.reset()
+        h.sweep_device(xd.data_ptr(), n)          # already dense: straight through the window kernels
+        assert np.array_equal(h.peaks(), brute)
+        assert h.stats()["dense_repeats"] == 1
+
+
 def test_dense_mode_two_tone_and_true_peak():
     """Config-1 material long enough to overflow the list (few-tone: a third of the samples survive the
     radius filter until the table has converged), digital and 4x true-peak: dense-mode tables equal
