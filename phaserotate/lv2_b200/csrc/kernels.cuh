@@ -1146,10 +1146,14 @@ __global__ void __launch_bounds__ (256) sweep_walk_kernel (const WinParams p)
 	const unsigned stride = gridDim.x * blockDim.x;
 	// whole warps per trip, reconverged at the top: a thread that leaves the rare walk below late must not
 	// drag its warp through the next point's window once more on its own
-	for (unsigned base = blockIdx.x * blockDim.x + (threadIdx.x & ~31u); base < n; base += stride) {
+	const float2*  lst    = p.list + (long long)c * p.list_stride;
+	const unsigned first  = blockIdx.x * blockDim.x + (threadIdx.x & ~31u);
+	float2         qn     = first + (threadIdx.x & 31u) < n ? lst[first + (threadIdx.x & 31u)] : make_float2 (0.f, 0.f);
+	for (unsigned base = first; base < n; base += stride) {
 		__syncwarp ();
-		const unsigned i  = base + (threadIdx.x & 31u);
-		const float2   q  = i < n ? p.list[(long long)c * p.list_stride + i] : make_float2 (0.f, 0.f);
+		const unsigned i = base + (threadIdx.x & 31u);
+		const float2   q = qn;
+		qn               = i + stride < n ? lst[i + stride] : make_float2 (0.f, 0.f); // the next trip's point: its latency hides behind this one
 		const float    ax = fabsf (q.x), ay = fabsf (q.y);
 		const float    tgs = fmaf (-2e-6f, ax + ay, tg); // global threshold less the slack of a comparison (2e-6 r at least)
 		// nearest grid angle: alpha = phi (mod pi)  <=>  j = -phi / step (mod MS); atan2 as in atan2_fast()
