@@ -57,6 +57,16 @@ with capi.Phaserot(n_channels=2, blksiz=8192, subsample=4) as h:
     h.sweep(s)
     h.peaks()
     print("dense repeats", h.stats()["dense_repeats"])
+    # the handle is dense now: two tones go through the walk beyond the first window (sector hopping, wide list)
+    tt = np.stack([0.5 * np.sin(2 * np.pi * 110 * t + c) + 0.25 * np.sin(2 * np.pi * 1760.3 * t) for c in (0.0, 1.0)], axis=1).astype(np.float32)
+    h.reset()
+    h.sweep(tt)
+    h.peaks()
+with capi.Phaserot(n_channels=1, blksiz=8192, subsample=50) as h:   # 0.02 degree grid: tables beyond shared memory, sector-window kernel
+    m = np.ascontiguousarray(np.concatenate([s[:, :1], s[:, :1], s[:, :1]]))
+    h.sweep(m)
+    h.peaks()
+    print("dense repeats (0.02 degree grid)", h.stats()["dense_repeats"])
 with capi.PhaserotGroup(2, [0, 0], n_channels=2, blksiz=8192) as g:
     g.sweep(x)
     assert np.array_equal(g.peaks(), a)
