@@ -1089,10 +1089,11 @@ __global__ void __launch_bounds__ (256) sweep_window_kernel (const WinParams p)
 //   * stops for good when |y_j| falls below the global threshold (the smallest sector threshold): no angle
 //     farther out can be raised;
 //   * jumps to the near edge of the next sector when |y_j| falls below the threshold of the sector j lies in:
-//     no angle farther out IN THAT SECTOR can be raised.
+//     no angle farther out IN THAT SECTOR can be raised;
+//   * gives the point to the wide list (sweep_kernel, every angle) after a dozen steps.
 // A point of a constant-envelope signal costs one atan2 and the handful of angles within reach of its own
-// sector's threshold; an interior point of a two-tone signal one evaluation per sector within reach of the
-// global threshold.  Margins: 4e-6 relative on every threshold and 2e-6 r absolute on every comparison (the fp32
+// sector's threshold; points well above the smallest threshold (interior points of a few-tone signal while the
+// table is young) are cheaper at every angle, angles in lanes, than step by step in one lane.  Margins: 4e-6 relative on every threshold and 2e-6 r absolute on every comparison (the fp32
 // evaluation of y is good to ~3e-7 r, so a value farther out can exceed the one that stopped the walk by at most
 // 6e-7 r); the walk starts one step beyond the nearest grid angle on either side, and the nearest grid angle is
 // found to 2e-5 rad (atan2_fast) + one rounding - far less than half a step for every grid whose tables fit
@@ -1108,6 +1109,11 @@ __device__ __forceinline__ float rcp_approx (float x)
 template <int WH> // half width of the window every point starts with, in grid angles
 __global__ void __launch_bounds__ (256) sweep_walk_kernel (const WinParams p)
 {
+	// A step of the walk costs a warp ~45 issue slots for one lane's benefit - 40 ps of the whole GPU - while
+	// sweep_kernel does a point at every angle in 200 ps: beyond half a dozen steps either side the wide list is
+	// the cheaper place, and a bounded walk also means no thread holds its CTA for 768 serial evaluations (which
+	// made launches with a few far-out points take 150-240 us for 10 us of work; ncu launch list, two tones).
+	constexpr int  kWalkEvals = 2 * WH + 1 + 12;
 	const int      c = p.chan0 + blockIdx.y;
 	const unsigned n = min (p.count[c], p.cap);
 	const int      MS = p.MS, G = MS / kSectors;
@@ -1204,9 +1210,9 @@ __global__ void __launch_bounds__ (256) sweep_walk_kernel (const WinParams p)
 					if (!(y >= tgs)) break;
 					// within reach of the sector's threshold: next angle; else on to the near edge of the next sector
 					t += (y >= s_sec[s] - (tg - tgs)) ? 1 : (dir ? j - s * G + 1 : (s + 1) * G - j);
-					if (done > kWideEvals) break;
+					if (done > kWalkEvals) break;
 				}
-				if (done > kWideEvals) {
+				if (done > kWalkEvals) {
 					wide = true; // what has been evaluated stays valid (a running maximum); the point is redone whole
 					break;
 				}

@@ -700,6 +700,13 @@ finish_pending (phaserot* h)
 	if (h->dense_mode && !h->pend_redone && !(h->cfg.flags & PHASEROT_FLAG_NO_PRUNE) && h->pend_points > 0 && (double)st[0] < 1e-3 * (double)h->pend_points) { // st[0]: points the lists held
 		h->dense_mode = false;
 	}
+	else if (!h->dense_mode && !(h->cfg.flags & PHASEROT_FLAG_NO_PRUNE) && h->pend_points >= (4ull << 20) && (double)st[1] > 5e-3 * (double)h->pend_points) {
+		// Few-tone material below the overflow limit (config 1's two tones: 1 % of the samples survive the radius
+		// filter): in normal mode every survivor was swept at every angle (st[1]).  The next sweep of this handle
+		// starts dense - windows instead of every angle - and stays so while its lists hold more than 0.1 % of the
+		// samples.  A mode of execution only: the table is the same bit for bit either way.
+		h->dense_mode = true;
+	}
 	h->pending      = false;
 	h->pend_exposed = false;
 	return PHASEROT_OK;
@@ -962,8 +969,16 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 	// angles it can still raise (sweep_window_kernel); what that leaves goes angles-in-lanes.
 	auto sweep_survivors = [&] (const unsigned* count, unsigned cap, bool boot) -> int {
 		if (A == 0) return PHASEROT_OK;
-		if (!dense || no_prune || boot) { // (bootstrap: the running peaks are still zero, every window would be the whole grid)
+		if (!dense || no_prune || (boot && !h->dense_mode)) {
 			return launch_sweep (h, A, c0, nchan, count, nullptr, cap, boot);
+		}
+		if (boot) {
+			// Bootstrap list of a dense handle (up to 1 M points per channel, 0.46 ms at every angle): the running
+			// peaks are still zero and every window would be the whole grid, so the head of the list is swept at
+			// every angle - and the whole list then goes through the windows like any other, against that table.
+			constexpr unsigned kBootBrute = 128u << 10;
+			const int          r          = launch_sweep (h, A, c0, nchan, count, nullptr, std::min (cap, kBootBrute), boot);
+			if (r) return r;
 		}
 		CK (cudaMemsetAsync (d_wide_count (h), 0, sizeof (unsigned) * 64, h->stream));
 		WinParams w;
