@@ -139,7 +139,10 @@ PHASEROT_API int phaserot_set_stream (phaserot_t* h, void* cuda_stream);
  * then repeated once in dense mode (launches sized to the list, and every
  * survivor evaluated only at the few angles it can still raise), the handle
  * stays in dense mode while the material needs it, and the table is the same
- * bit for bit either way (phaserot_stats_t.dense_repeats counts the repeats). */
+ * bit for bit either way (phaserot_stats_t.dense_repeats counts the repeats).
+ * A handle also starts its NEXT sweep in dense mode, without a repeat, when a
+ * finished sweep put more than 0.5 % of its samples on the lists, and returns
+ * to normal mode once the lists hold less than 0.1 %. */
 PHASEROT_API int phaserot_sweep (phaserot_t* h, const float* interleaved, uint64_t n_frames,
                                  int ang_start, int ang_end, int ang_stride, int chn);
 
