@@ -346,6 +346,37 @@ def test_dense_mode_grids_and_envelopes(subsample, nch, material):
         assert h.stats()["dense_repeats"] == 1
 
 
+def test_dense_mode_window_kernel_fallback_equals_walk_kernel(tmp_path):
+    """PHASEROT_WALK=0 sends every dense-mode grid through sweep_window_kernel (the kernel finer grids and
+    partial angle sets still use); the switch is read once per process, so the other setting runs in a child.
+    Same table bit for bit from both kernels on a 0.1 degree grid."""
+    import sys
+    import torch
+    x = _tones(100.0, [(0.5, 440.0, [0.0, 1.0])])
+    xd = torch.from_numpy(x).cuda()
+    with capi.Phaserot(n_channels=2, blksiz=8192, subsample=10) as h:
+        h.sweep_device(xd.data_ptr(), x.shape[0])
+        here = h.peaks()
+        assert h.stats()["dense_repeats"] == 1
+    out = tmp_path / "pk.npy"
+    code = (
+        "import sys, numpy as np, torch\n"
+        "sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from phaserotate.lv2_b200 import capi\n"
+        "import test_gpu_round2 as T\n"
+        "x = T._tones(100.0, [(0.5, 440.0, [0.0, 1.0])])\n"
+        "xd = torch.from_numpy(x).cuda()\n"
+        "h = capi.Phaserot(n_channels=2, blksiz=8192, subsample=10)\n"
+        "h.sweep_device(xd.data_ptr(), x.shape[0])\n"
+        "np.save(%r, h.peaks())\n"
+        "assert h.stats()['dense_repeats'] == 1\n"
+    ) % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)), str(out))
+    env = dict(os.environ, PHASEROT_WALK="0")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert np.array_equal(np.load(out), here)
+
+
 def test_dense_mode_two_tone_and_true_peak():
     """Config-1 material long enough to overflow the list (few-tone: a third of the samples survive the
     radius filter until the table has converged), digital and 4x true-peak: dense-mode tables equal
