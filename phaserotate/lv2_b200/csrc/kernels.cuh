@@ -1082,22 +1082,24 @@ __global__ void __launch_bounds__ (256) sweep_window_kernel (const WinParams p)
 }
 
 // The same sweep when the swept set is the whole grid, or all of it but an angle or two (the CLI's sweep leaves
-// out angle 0; slot = grid index - slot_base), without a single acos: |y_j| = r |cos (alpha_j - phi)| falls monotonically with the distance of j from the direction of the
-// point, out to 90 degrees on either side.  The thread evaluates the grid angle nearest to phi, then walks
-// outwards in both directions: every visited angle is evaluated (sweep_kernel's fp32 expression) and compared
-// with the running peak; the walk
-//   * stops for good when |y_j| falls below the global threshold (the smallest sector threshold): no angle
-//     farther out can be raised;
+// out angle 0; slot = grid index - slot_base), without a single acos: |y_j| = r |cos (alpha_j - phi)| falls
+// monotonically with the distance of j from the direction of the point, out to 90 degrees on either side.  Every
+// thread of a warp evaluates the 2 WH + 1 grid angles around the one nearest to phi (sweep_kernel's fp32
+// expression, compared with the running peak); if both ends of that window lie below the global threshold (the
+// smallest sector threshold) no angle farther out can be raised and the point is done.  Otherwise the thread
+// walks outwards from the window, in both directions; the walk
+//   * stops for good when |y_j| falls below the global threshold;
 //   * jumps to the near edge of the next sector when |y_j| falls below the threshold of the sector j lies in:
 //     no angle farther out IN THAT SECTOR can be raised;
 //   * gives the point to the wide list (sweep_kernel, every angle) after a dozen steps.
-// A point of a constant-envelope signal costs one atan2 and the handful of angles within reach of its own
-// sector's threshold; points well above the smallest threshold (interior points of a few-tone signal while the
-// table is young) are cheaper at every angle, angles in lanes, than step by step in one lane.  Margins: 4e-6 relative on every threshold and 2e-6 r absolute on every comparison (the fp32
-// evaluation of y is good to ~3e-7 r, so a value farther out can exceed the one that stopped the walk by at most
-// 6e-7 r); the walk starts one step beyond the nearest grid angle on either side, and the nearest grid angle is
-// found to 2e-5 rad (atan2_fast) + one rounding - far less than half a step for every grid whose tables fit
-// shared memory (the condition for this kernel; finer grids keep sweep_window_kernel).
+// A point of a constant-envelope signal costs one atan2 and the first window; points well above the smallest
+// threshold (interior points of a few-tone signal while the table is young) are cheaper at every angle, angles in
+// lanes, than step by step in one lane.  Margins: 4e-6 relative on every threshold and 2e-6 (|x| + |h|) >= 2e-6 r
+// absolute on every comparison (the fp32 evaluation of y is good to ~3e-7 r, so a value farther out can exceed
+// the one that stopped the walk by at most 6e-7 r); window and walk start beyond the nearest grid angle on either
+// side, and the nearest grid angle is found to 2e-5 rad (the atan2 polynomial) + one rounding - far less than
+// half a step for every grid whose table fits shared memory (the condition for this kernel; finer grids keep
+// sweep_window_kernel).
 // MUFU.RCP / one instruction
 __device__ __forceinline__ float rcp_approx (float x)
 {
