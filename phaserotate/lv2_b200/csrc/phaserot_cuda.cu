@@ -838,8 +838,12 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 	// has landed.)
 	const int       OS         = h->OS;
 	const long long ppseg      = (long long)h->V * 2 * (OS > 1 ? OS + 1 : 1); // points a segment can put on the list (true-peak: the sample and OS interpolated points)
-	long long       segs_first = std::max<long long> (1, ((long long)h->n_sm * 8) / nchan);
-	long long       segs_max   = !src_is_device ? segs_first : (OS_is_digital (h) ? 16 : 2) * segs_first;
+	// (PHASEROT_SEGS_FIRST = segments per CTA of the first contiguous launch, PHASEROT_SEGS_MULT = size of the
+	// following launches in units of it: measurement aids, defaults 8 and 16)
+	static const int k_first = getenv ("PHASEROT_SEGS_FIRST") ? std::max (1, atoi (getenv ("PHASEROT_SEGS_FIRST"))) : 8;
+	static const int k_mult  = getenv ("PHASEROT_SEGS_MULT") ? std::max (1, atoi (getenv ("PHASEROT_SEGS_MULT"))) : 16;
+	long long       segs_first = std::max<long long> (1, ((long long)h->n_sm * k_first) / nchan);
+	long long       segs_max   = !src_is_device ? segs_first : (OS_is_digital (h) ? k_mult : 2) * segs_first;
 	// Survivor list, sized by demand.  Normal mode: 1/32 of the points of the
 	// largest launch (pruning leaves 1e-4 .. 1e-5 of them on programme material), at
 	// least 1 M points per channel; a list that overflows flags the pass and
