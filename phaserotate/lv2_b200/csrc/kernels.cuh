@@ -959,6 +959,7 @@ struct WinParams {
 	unsigned long long* n_listed; // statistics: points on the lists of this sweep
 	int             slot_base; // >= 0: the swept set is a run of consecutive grid indices, slot = grid index - slot_base (no table)
 	int             smem_tables; // 1: (ca, sa) and a snapshot of the running peaks sit in shared memory (A * 12 bytes)
+	int             walk_steps;  // sweep_walk_kernel: evaluations beyond the first window before a point goes to the wide list
 	int             A;
 };
 
@@ -1115,7 +1116,7 @@ __global__ void __launch_bounds__ (256) sweep_walk_kernel (const WinParams p)
 	// sweep_kernel does a point at every angle in 200 ps: beyond half a dozen steps either side the wide list is
 	// the cheaper place, and a bounded walk also means no thread holds its CTA for 768 serial evaluations (which
 	// made launches with a few far-out points take 150-240 us for 10 us of work; ncu launch list, two tones).
-	constexpr int  kWalkEvals = 2 * WH + 1 + 12;
+	const int      kWalkEvals = 2 * WH + 1 + p.walk_steps; // a dozen by default
 	const int      c = p.chan0 + blockIdx.y;
 	const unsigned n = min (p.count[c], p.cap);
 	const int      MS = p.MS, G = MS / kSectors;

@@ -980,7 +980,7 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 			// Bootstrap list of a dense handle (up to 1 M points per channel, 0.46 ms at every angle): the running
 			// peaks are still zero and every window would be the whole grid, so the head of the list is swept at
 			// every angle - and the whole list then goes through the windows like any other, against that table.
-			constexpr unsigned kBootBrute = 128u << 10;
+			static const unsigned kBootBrute = getenv ("PHASEROT_BOOT_BRUTE") ? (unsigned)atoi (getenv ("PHASEROT_BOOT_BRUTE")) : 128u << 10;
 			const int          r          = launch_sweep (h, A, c0, nchan, count, nullptr, std::min (cap, kBootBrute), boot);
 			if (r) return r;
 		}
@@ -1023,6 +1023,8 @@ sweep_core (phaserot* h, const float* src, bool src_is_device, long long n_frame
 				static const double wrad = getenv ("PHASEROT_WALK_RAD") ? atof (getenv ("PHASEROT_WALK_RAD")) : 5e-3;
 				const int  wh = (int)ceil (wrad * h->MS / M_PI); // half width of the first window: 5e-3 rad in grid angles (reaches points up to 7e-6 above the threshold)
 				const size_t tsm = (size_t)A * sizeof (float4);
+				static const int wsteps = getenv ("PHASEROT_WALK_STEPS") ? atoi (getenv ("PHASEROT_WALK_STEPS")) : 12;
+				w.walk_steps     = wsteps;
 				if (wh <= 1) sweep_walk_kernel<1><<<wg, 256, tsm, h->stream>>> (w);
 				else if (wh <= 2) sweep_walk_kernel<2><<<wg, 256, tsm, h->stream>>> (w);
 				else if (wh <= 3) sweep_walk_kernel<3><<<wg, 256, tsm, h->stream>>> (w);
